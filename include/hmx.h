@@ -1,0 +1,161 @@
+/*
+ * hmx.h -- C ABI of libhamilton.so: the B200-native (sm_100a) implementation of the Stage-1 TMCMC
+ * likelihood hot path of keisuke58/Tmcmc202601.
+ *
+ * The reference has no FFI: its "plugin" interface is duck-typed Python.  Each entry
+ * point below names the reference interface it replaces (paths relative to the reference root):
+ *   S5 = tmcmc/program2602/improved_5species_jit.py      S4 = tmcmc/program2602/improved1207_paper_jit.py
+ *   EV = data_5species/core/evaluator.py                  TM = data_5species/core/tmcmc.py
+ *   MAIN = data_5species/main/estimate_reduced_nishioka.py
+ * The ctypes binding a maintainer would add on the reference side is shown in INTEGRATION.md; this
+ * repository's own binding is tmcmc202601_b200/_abi.py.
+ *
+ * Conventions
+ *   - plain C, no exceptions: every call returns 0 on success or a negative hmx_status; the message is
+ *     available from hmx_last_error().
+ *   - every array argument is caller-owned and may be a HOST pointer (pageable or pinned) or a DEVICE
+ *     pointer on the context's GPU (detected with cudaPointerGetAttributes).  Host inputs are staged
+ *     through pinned buffers owned by the context; a call with any host OUTPUT pointer returns after the
+ *     results have landed (stream-synchronised); a call whose outputs are all device pointers only
+ *     enqueues work on the context stream (hmx_set_stream / hmx_synchronize).
+ *   - one context per process and GPU; calls on one context serialise (not thread-safe, like the
+ *     reference evaluator whose histories are mutable).
+ *   - failed solves follow the reference's error convention: logL = -1e20, never an error return
+ *     (EV:655,667,753; TM:306).
+ *   - there is NO CPU fallback: hmx_create fails when no sm_100 device is present.
+ */
+#ifndef HMX_H
+#define HMX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMX_ABI_VERSION 1
+#define HMX_NSTATE 12  /* g = [phi_1..5, phi_0, psi_1..5, gamma]  (S5:8-13) */
+#define HMX_NTHETA 20  /* S5:15-22 */
+#define HMX_MAX_OBS 8
+#define HMX_MAX_COND 8
+
+typedef enum {
+    HMX_OK = 0,
+    HMX_ERR_INVALID = -1,   /* bad argument */
+    HMX_ERR_CUDA = -2,      /* CUDA runtime error (message has the cudaError string) */
+    HMX_ERR_NO_DEVICE = -3, /* no sm_100 GPU visible: the product path refuses to run */
+    HMX_ERR_OOM = -4
+} hmx_status;
+
+/* status word per evaluation (hmx_loglik_batch `status`) */
+#define HMX_ST_NONFINITE 1u /* trajectory / likelihood inputs non-finite -> logL = -1e20 (EV:657-667,747-753) */
+#define HMX_ST_MAXITER 2u   /* a time step exhausted max_newton_iter (S5:308) */
+#define HMX_ST_SINGULAR 4u  /* a Newton direction came out non-finite (the reference's LinAlgError/ridge path, S5:369-373) */
+
+/* One experimental condition: what LogLikelihoodEvaluator.__init__ receives (EV:381-398) plus the
+ * per-condition initial state from the loader (MAIN:1907-1928). */
+typedef struct {
+    double phi_init[5];                /* solver_kwargs["phi_init"], scalar already broadcast (S5:489-495) */
+    int32_t n_obs;                     /* rows of `data` (5 with --use-exp-init, 6 in older run dirs) */
+    int32_t idx_sparse[HMX_MAX_OBS];   /* row indices into the trajectory, 0..n_steps (MAIN:1827-1867) */
+    double data[HMX_MAX_OBS * 5];      /* row-major [n_obs,5] */
+    double sigma_obs[HMX_MAX_OBS * 5]; /* scalar / [5] sigma pre-broadcast to [n_obs,5] (EV:286-290) */
+    double weights[HMX_MAX_OBS * 5];   /* 1.0 where the reference passes weights=None (EV:332) */
+    double cov_rel;                    /* BiofilmTSM.cov_rel (S4:1067) */
+    uint32_t active_theta_mask;        /* bit k set <=> k in BiofilmTSM.active_idx (S4:1075) */
+    int32_t use_absolute_volume;       /* EV:703-711: mu = phi*gamma instead of phi*psi */
+    int32_t tsm_variance;              /* 1 = EV:700-745 variance (evaluator parity), 0 = deterministic only */
+} hmx_cond;
+
+/* mirrors solver_kwargs (MAIN:1919-1928) + BiofilmNewtonSolver5S.__init__ defaults (S5:464-511) */
+typedef struct {
+    int32_t abi_version; /* must be HMX_ABI_VERSION */
+    double dt;
+    int32_t n_steps; /* maxtimestep */
+    double eps;      /* 1e-6 */
+    double Kp1;
+    double c_const;
+    double alpha_const;
+    double K_hill;
+    double n_hill;
+    int32_t max_newton_iter; /* 50 */
+    double eta[5];
+    double eta_phi[5];
+    int32_t active_species_mask; /* bit i <=> species i active in the initial state (S5:566-575) */
+    int32_t n_cond;              /* 1..HMX_MAX_COND */
+    hmx_cond cond[HMX_MAX_COND];
+} hmx_config;
+
+typedef struct hmx_ctx hmx_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------------------------ */
+/* replaces: BiofilmNewtonSolver5S(**solver_kwargs) + LogLikelihoodEvaluator(...) construction
+ * (S5:464-511, EV:381-490).  Uploads the constants to __constant__ memory of `device`. */
+int hmx_create(hmx_ctx** ctx, const hmx_config* cfg, int32_t device);
+void hmx_destroy(hmx_ctx* ctx);
+/* message of the last failing call on ctx (ctx may be NULL: last hmx_create failure) */
+const char* hmx_last_error(const hmx_ctx* ctx);
+/* run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); NULL = context stream */
+int hmx_set_stream(hmx_ctx* ctx, void* cuda_stream);
+int hmx_synchronize(hmx_ctx* ctx);
+int hmx_abi_version(void);
+
+/* ---- the hot path -------------------------------------------------------------------------------- */
+/* replaces: evaluate_particles_parallel(LogLikelihoodEvaluator, theta) (TM:247-312) for FULL 20-vectors:
+ * per evaluation BiofilmTSM.solve_tsm -> run_deterministic (S5:561-581, 837-882; S4:1077-1160) and
+ * LogLikelihoodEvaluator.__call__ from EV:645 on (guards, mu/var at idx_sparse, log_likelihood_sparse
+ * EV:237-371 with rho=0).  The theta_sub -> theta_full map of EV:635-637 stays on the host side.
+ *   theta        [N,20] row-major
+ *   cond_id      [N] int32 index into cfg.cond, or NULL (= condition 0)
+ *   logL         [N]
+ *   obs_state    [N,n_obs_max,12] trajectory rows at idx_sparse (n_obs_max = max n_obs over conditions), or NULL
+ *   status       [N] HMX_ST_* bits, or NULL
+ *   newton_iters [N] quasi-Newton iterations summed over the time steps, or NULL */
+int hmx_loglik_batch(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, int64_t N,
+                     double* logL, double* obs_state, uint32_t* status, uint32_t* newton_iters);
+
+/* replaces: BiofilmNewtonSolver5S.run_deterministic / .solve (S5:561-581, 646) for a batch.
+ *   g [N,n_steps+1,12] row-major;  t_arr is (arange(n_steps+1) * dt) and is left to the caller. */
+int hmx_trajectory_batch(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, int64_t N,
+                         double* g, uint32_t* status, uint32_t* newton_iters);
+
+/* ---- per-stage TMCMC arithmetic ------------------------------------------------------------------ */
+/* replaces: the 25-step ESS bisection for delta-beta (TM:613-659, beta_schedule="ess"). ess_at_lo is NaN
+ * when no bisection step was accepted (the reference's ess_at_delta_low = None). */
+int hmx_beta_step(hmx_ctx* ctx, const double* logL, int64_t N, double beta, double target_ess_ratio,
+                  double min_delta_beta, double max_delta_beta, double* delta_beta, double* ess_at_lo);
+/* replaces: weights + evidence increment (TM:686-701). delta_beta is (beta_next - beta) as the reference
+ * forms it.  *log_Sj is NaN and w uniform when the reference would fall back ("Weight sum issue"). */
+int hmx_weights(hmx_ctx* ctx, const double* logL, int64_t N, double delta_beta, double* w, double* log_Sj);
+/* replaces: systematic_resample (TM:186-198) with the uniform draw u = rng.random() supplied by the host.
+ * idx [N] int64, bit-exact with NumPy for identical (w, u). */
+int hmx_resample(hmx_ctx* ctx, const double* w, int64_t N, double u, int64_t* idx);
+/* replaces: np.cov(theta.T, aweights=w) at TM:766 (ddof=1).  mean [d] (may be NULL), cov [d,d]. */
+int hmx_weighted_cov(hmx_ctx* ctx, const double* theta, const double* w, int64_t N, int32_t d,
+                     double* mean, double* cov);
+/* the two shard-local halves of hmx_weighted_cov for particles sharded over GPUs: the host all-reduces
+ * `moments` (2+d doubles: sum w, sum w^2, sum w*theta_j) between them, then all-reduces `scatter` (d*d). */
+int hmx_weighted_moments(hmx_ctx* ctx, const double* theta, const double* w, int64_t N, int32_t d,
+                         double* moments);
+int hmx_weighted_scatter(hmx_ctx* ctx, const double* theta, const double* w, int64_t N, int32_t d,
+                         const double* mean, double* scatter);
+
+/* ---- measurement support ------------------------------------------------------------------------- */
+typedef struct {
+    int64_t evals;         /* evaluations processed by the last hmx_loglik_batch / hmx_trajectory_batch */
+    int64_t newton_iters;  /* sum of quasi-Newton iterations (direction solves) */
+    int64_t q_evals;       /* residual evaluations = state-machine trips (iteration starts + line-search trials) */
+    int64_t kernel_launches; /* CUDA kernels launched by this context since creation */
+    double last_ode_kernel_ms; /* CUDA-event duration of the ODE kernel of the last batch (0 if not timed) */
+} hmx_counters;
+/* synchronises the stream */
+int hmx_get_counters(hmx_ctx* ctx, hmx_counters* out);
+/* enable CUDA-event timing of the ODE kernel inside hmx_loglik_batch (adds two event records) */
+int hmx_set_timing(hmx_ctx* ctx, int32_t enabled);
+/* register-resident DFMA loop: measured FP64 FMA peak of this GPU in TFLOP/s (roofline denominator) */
+int hmx_measure_fp64_peak(hmx_ctx* ctx, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMX_H */

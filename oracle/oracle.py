@@ -287,3 +287,50 @@ def weighted_cov(theta, w):
     mean, cov = np.empty(d), np.empty((d, d))
     lib().orc_weighted_cov(_dptr(theta), _dptr(w), C.c_int64(N), C.c_int(d), _dptr(mean), _dptr(cov))
     return mean, cov
+
+
+def from_hmx_config(hcfg):
+    """(SolverCfg, [CondCfg...]) equivalent to a product-side HmxConfig (tmcmc202601_b200/_abi.py).
+
+    The oracle's solver struct carries ONE phi_init, the product config one per condition; this returns a
+    list of (SolverCfg, CondCfg) pairs, one per condition.
+    """
+    out = []
+    for k in range(hcfg.n_cond):
+        hc = hcfg.cond[k]
+        scfg = make_solver_cfg(
+            dt=hcfg.dt, maxtimestep=hcfg.n_steps, eps=hcfg.eps, Kp1=hcfg.Kp1, c_const=hcfg.c_const,
+            alpha_const=hcfg.alpha_const, K_hill=hcfg.K_hill, n_hill=hcfg.n_hill,
+            max_newton_iter=hcfg.max_newton_iter, eta_vec=list(hcfg.eta), eta_phi_vec=list(hcfg.eta_phi),
+            phi_init=list(hc.phi_init), active_species=[i for i in range(5) if (hcfg.active_species_mask >> i) & 1],
+        )
+        n = hc.n_obs
+        cc = make_cond_cfg(
+            np.array(hc.data[: n * 5]).reshape(n, 5), list(hc.idx_sparse[:n]), np.array(hc.sigma_obs[: n * 5]).reshape(n, 5),
+            cov_rel=hc.cov_rel, active_theta_indices=[j for j in range(NTHETA) if (hc.active_theta_mask >> j) & 1],
+            weights=np.array(hc.weights[: n * 5]).reshape(n, 5), use_absolute_volume=bool(hc.use_absolute_volume),
+            tsm_variance=bool(hc.tsm_variance),
+        )
+        out.append((scfg, cc))
+    return out
+
+
+def evaluate_hmx(hcfg, theta, cond_id=None, n_threads=None, details=False):
+    """Oracle evaluation of a product-side batch: logL[N] for theta[N,20], cond_id[N] (None = 0)."""
+    theta = _f64(theta)
+    N = theta.shape[0]
+    cid = np.zeros(N, dtype=np.int32) if cond_id is None else np.asarray(cond_id, dtype=np.int32)
+    pairs = from_hmx_config(hcfg)
+    logL = np.empty(N)
+    status = np.zeros(N, dtype=np.uint32)
+    its = np.zeros(N, dtype=np.int64)
+    tr = np.zeros(N, dtype=np.int64)
+    for k, (scfg, cc) in enumerate(pairs):
+        sel = np.nonzero(cid == k)[0]
+        if sel.size == 0:
+            continue
+        l, s, i, t = evaluate_batch(scfg, [cc], theta[sel], None, n_threads=n_threads, details=True)
+        logL[sel], status[sel], its[sel], tr[sel] = l, s, i, t
+    if details:
+        return logL, status, its, tr
+    return logL

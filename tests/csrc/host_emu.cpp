@@ -1,0 +1,99 @@
+// host_emu.cpp -- CPU emulation of ONE GPU lane, for tests only.
+//
+// Compiles the product's __host__ __device__ arithmetic (tmcmc202601_b200/csrc/hmx_{model,lane,obs}.cuh)
+// with g++ so the structured direction solve and the lane state machine can be compared with the dense
+// oracle on machines without a GPU (`pytest -m "not gpu"`).  It is NOT part of libhamilton.so and is never
+// loaded by the product package: there is no CPU fallback on the product path.
+#include <stdint.h>
+#include <string.h>
+
+#include "../../tmcmc202601_b200/csrc/hmx_obs.cuh"
+
+using namespace hmx;
+
+template <bool ALPHA, int HILL>
+static void run_lane(const SolverConsts& K, const CondConsts& C, const ThetaMap& TM, const double* theta,
+                     double* g_arr, double* logL, uint32_t* status, uint32_t* iters, uint32_t* trips) {
+    Lane s;
+    lane_init(K, s, theta, C.g0);
+    if (g_arr) memcpy(g_arr, s.g, 12 * sizeof(double));
+    double pairs[HMX_MAX_OBS * kPairStride];
+    memset(pairs, 0, sizeof(pairs));
+    bool done = false;
+    while (!done) {
+        if (lane_trip<ALPHA, HILL>(K, s)) {
+            double old[11];
+            memcpy(old, s.gp, sizeof(old));
+            done = lane_advance(K, s);
+            if (g_arr) memcpy(g_arr + (size_t)s.step_idx * 12, s.g, 12 * sizeof(double));
+            for (int o = 0; o < C.n_obs; ++o) {
+                const int t = C.idx[o] < 1 ? 1 : C.idx[o];
+                if (t == s.step_idx) {
+                    memcpy(pairs + o * kPairStride, s.g, 12 * sizeof(double));
+                    memcpy(pairs + o * kPairStride + 12, old, 11 * sizeof(double));
+                }
+            }
+        }
+    }
+    uint32_t st = s.status;
+    if (logL) *logL = obs_loglik<ALPHA, HILL>(K, C, TM, theta, pairs, s.status, nullptr, &st);
+    if (status) *status = st;
+    if (iters) *iters = s.iters;
+    if (trips) *trips = s.trips;
+}
+
+template <bool ALPHA, int HILL>
+static void dir_once(const SolverConsts& K, const double* theta, const double* g_new, const double* g_old,
+                     double* Q, double* delta) {
+    double A[15], b[5], x[12], gp[11];
+    theta_to_Ab(theta, A, b);
+    for (int i = 0; i < 12; ++i) x[i] = g_new[i];
+    for (int i = 0; i < 11; ++i) gp[i] = g_old[i];
+    Eval e;
+    residual<ALPHA, HILL>(K, x, gp, A, b, e);
+    for (int i = 0; i < 12; ++i) Q[i] = e.Q[i];
+    double d[12];
+    direction<ALPHA, HILL>(K, e, A, b, d);
+    for (int i = 0; i < 12; ++i) delta[i] = d[i];
+}
+
+#define DISPATCH(FN, ...)                                   \
+    do {                                                    \
+        const bool al = (K.alpha != 0.0);                   \
+        const int hv = hill_variant(K);                     \
+        if (al) {                                           \
+            if (hv == 0) FN<true, 0>(__VA_ARGS__);          \
+            else if (hv == 1) FN<true, 1>(__VA_ARGS__);     \
+            else FN<true, 2>(__VA_ARGS__);                  \
+        } else {                                            \
+            if (hv == 0) FN<false, 0>(__VA_ARGS__);         \
+            else if (hv == 1) FN<false, 1>(__VA_ARGS__);    \
+            else FN<false, 2>(__VA_ARGS__);                 \
+        }                                                   \
+    } while (0)
+
+extern "C" {
+
+// full solve of one (theta, condition): trajectory (optional), logL, counters
+int emu_evaluate(const hmx_config* cfg, int cond, const double* theta, double* g_arr, double* logL,
+                 uint32_t* status, uint32_t* iters, uint32_t* trips) {
+    const char* why;
+    if (validate_config(cfg, &why) != 0) return -1;
+    SolverConsts K;
+    CondConsts C;
+    make_solver_consts(*cfg, K);
+    make_cond_consts(*cfg, cond, C);
+    ThetaMap TM = {HMX_THETA_P, HMX_THETA_Q};
+    DISPATCH(run_lane, K, C, TM, theta, g_arr, logL, status, iters, trips);
+    return 0;
+}
+
+// residual and structured quasi-Newton direction at one point
+int emu_direction(const hmx_config* cfg, const double* theta, const double* g_new, const double* g_old,
+                  double* Q, double* delta) {
+    SolverConsts K;
+    make_solver_consts(*cfg, K);
+    DISPATCH(dir_once, K, theta, g_new, g_old, Q, delta);
+    return 0;
+}
+}

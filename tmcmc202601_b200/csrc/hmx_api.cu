@@ -1,0 +1,651 @@
+// hmx_api.cu -- C ABI (include/hmx.h) over the sm_100a kernels.  Build: see __graft_entry__.build().
+//
+// Memory model: every array argument may be a host or a device pointer.  Host inputs are copied to
+// context-owned device buffers with cudaMemcpyAsync on the context stream; host outputs are copied back
+// and the call synchronises the stream before returning.  Device pointers are used in place and the call
+// only enqueues work.  Scratch (observation pairs, status words, counters, reduction partials) lives in
+// growable device buffers owned by the context, sized for 180 GB HBM3e: the per-evaluation footprint is
+// 20*8 (theta) + n_obs*24*8 (pairs) + 3*4 (status/iters/trips) + 8 (logL) bytes ~= 1.1 KB, so one 4 Mi-evaluation
+// chunk needs ~4.6 GB.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+
+#include "../../include/hmx.h"
+#include "hmx_consts.h"
+#include "hmx_kernels.cuh"
+#include "hmx_stage.cuh"
+
+using namespace hmx;
+
+namespace {
+
+constexpr long long kChunkEvals = 1ll << 22;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+struct hmx_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    hmx_config cfg;
+    SolverConsts K;
+    CondConsts C[HMX_MAX_COND];
+    OdeCond oc[HMX_MAX_COND];
+    int n_obs_max = 0;
+    bool alpha = false;
+    int hill = 0;
+    int ode_blocks_per_sm = 1;
+    std::string err;
+
+    // device scratch
+    DevBuf theta, cond_id, pairs, status, iters, trips, logL, obs_state, traj;
+    DevBuf st_in0, st_in1, st_in2, st_out0, st_out1, partial, cs;
+    CondConsts* d_cond = nullptr;
+    unsigned long long* d_counters = nullptr;  // [0] work counter, [1] sum iters, [2] sum trips
+    StageState* d_stage = nullptr;
+    unsigned int* d_tickets = nullptr;  // [64]
+    double* d_small = nullptr;          // [2048] moments / mean / scatter / small outputs
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timing = false;
+    bool timing_pending = false;
+    double last_ode_ms = 0.0;
+    long long last_evals = 0;
+    long long launches = 0;
+};
+
+namespace {
+
+int fail(hmx_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(ctx, HMX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+    } while (0)
+
+int ensure(hmx_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, HMX_ERR_OOM, std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return 0;
+}
+
+bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// input: returns a device pointer valid on ctx->stream (the original one, or a staged copy)
+int stage_in(hmx_ctx* ctx, const void* p, size_t bytes, DevBuf& buf, const void** out) {
+    if (!p) {
+        *out = nullptr;
+        return 0;
+    }
+    if (is_device_ptr(p)) {
+        *out = p;
+        return 0;
+    }
+    int rc = ensure(ctx, buf, bytes);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(buf.p, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *out = buf.p;
+    return 0;
+}
+
+// output: device pointer to write to; *host_dst set when a copy-back is needed afterwards
+int stage_out(hmx_ctx* ctx, void* p, size_t bytes, DevBuf& buf, void** dev, void** host_dst) {
+    *host_dst = nullptr;
+    if (!p) {
+        *dev = nullptr;
+        return 0;
+    }
+    if (is_device_ptr(p)) {
+        *dev = p;
+        return 0;
+    }
+    int rc = ensure(ctx, buf, bytes);
+    if (rc) return rc;
+    *dev = buf.p;
+    *host_dst = p;
+    return 0;
+}
+
+int red_blocks(long long N) {
+    long long b = (N + (long long)kRedThreads * 4 - 1) / ((long long)kRedThreads * 4);
+    return (int)std::max(1ll, std::min<long long>(b, kRedMaxBlocks));
+}
+
+template <bool ALPHA, int HILL>
+void launch_ode(hmx_ctx* ctx, const OdeParams& P, int blocks) {
+    ode_kernel<ALPHA, HILL><<<blocks, kOdeThreads, 0, ctx->stream>>>(P);
+}
+template <bool ALPHA, int HILL>
+void launch_obs(hmx_ctx* ctx, const ObsParams& P, int blocks) {
+    obs_kernel<ALPHA, HILL><<<blocks, 128, 0, ctx->stream>>>(P);
+}
+template <bool ALPHA, int HILL>
+int ode_occupancy() {
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ode_kernel<ALPHA, HILL>, kOdeThreads, 0);
+    return nb;
+}
+
+#define HMX_DISPATCH(FN, ...)                                  \
+    do {                                                       \
+        if (ctx->alpha) {                                      \
+            if (ctx->hill == 0) FN<true, 0>(__VA_ARGS__);      \
+            else if (ctx->hill == 1) FN<true, 1>(__VA_ARGS__); \
+            else FN<true, 2>(__VA_ARGS__);                     \
+        } else {                                               \
+            if (ctx->hill == 0) FN<false, 0>(__VA_ARGS__);     \
+            else if (ctx->hill == 1) FN<false, 1>(__VA_ARGS__);\
+            else FN<false, 2>(__VA_ARGS__);                    \
+        }                                                      \
+    } while (0)
+
+int query_occupancy(hmx_ctx* ctx) {
+    int nb = 0;
+    if (ctx->alpha) {
+        nb = ctx->hill == 0 ? ode_occupancy<true, 0>() : ctx->hill == 1 ? ode_occupancy<true, 1>() : ode_occupancy<true, 2>();
+    } else {
+        nb = ctx->hill == 0 ? ode_occupancy<false, 0>() : ctx->hill == 1 ? ode_occupancy<false, 1>() : ode_occupancy<false, 2>();
+    }
+    return std::max(nb, 1);
+}
+
+// the ODE solve + observation likelihood for one chunk of evaluations already resident on the device
+int run_chunk(hmx_ctx* ctx, const double* d_theta, const int32_t* d_cond, long long N, double* d_logL,
+              double* d_obs_state, uint32_t* d_status, uint32_t* d_iters, double* d_traj, bool want_logL) {
+    int rc;
+    const long long pair_stride = (long long)std::max(ctx->n_obs_max, 1) * kPairStride;
+    if ((rc = ensure(ctx, ctx->pairs, (size_t)N * pair_stride * sizeof(double)))) return rc;
+    if ((rc = ensure(ctx, ctx->trips, (size_t)N * sizeof(uint32_t)))) return rc;
+    if (!d_status) {
+        if ((rc = ensure(ctx, ctx->status, (size_t)N * sizeof(uint32_t)))) return rc;
+        d_status = (uint32_t*)ctx->status.p;
+    }
+    if (!d_iters) {
+        if ((rc = ensure(ctx, ctx->iters, (size_t)N * sizeof(uint32_t)))) return rc;
+        d_iters = (uint32_t*)ctx->iters.p;
+    }
+    CU(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));  // work counter only
+
+    OdeParams P;
+    P.K = ctx->K;
+    for (int k = 0; k < HMX_MAX_COND; ++k) P.cond[k] = ctx->oc[k];
+    P.theta = d_theta;
+    P.cond_id = d_cond;
+    P.N = N;
+    P.pairs = (double*)ctx->pairs.p;
+    P.pair_stride = pair_stride;
+    P.traj = d_traj;
+    P.status = d_status;
+    P.iters = d_iters;
+    P.trips = (uint32_t*)ctx->trips.p;
+    P.work_counter = ctx->d_counters;
+    P.totals = ctx->d_counters + 1;
+
+    const long long want_blocks = (N + kOdeThreads - 1) / kOdeThreads;
+    const int blocks = (int)std::min<long long>(want_blocks, (long long)ctx->sm_count * ctx->ode_blocks_per_sm);
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    HMX_DISPATCH(launch_ode, ctx, P, blocks);
+    CU(cudaGetLastError());
+    ++ctx->launches;
+    if (ctx->timing) {
+        CU(cudaEventRecord(ctx->ev1, ctx->stream));
+        ctx->timing_pending = true;
+    }
+
+    if (want_logL) {
+        ObsParams O;
+        O.K = ctx->K;
+        ThetaMap tm = {HMX_THETA_P, HMX_THETA_Q};
+        O.TM = tm;
+        O.cond = ctx->d_cond;
+        O.theta = d_theta;
+        O.cond_id = d_cond;
+        O.N = N;
+        O.pairs = (const double*)ctx->pairs.p;
+        O.pair_stride = pair_stride;
+        O.status_in = d_status;
+        O.status_out = d_status;
+        O.logL = d_logL;
+        O.obs_state = d_obs_state;
+        O.obs_stride = (long long)std::max(ctx->n_obs_max, 1) * 12;
+        const int ob = (int)((N + 127) / 128);
+        HMX_DISPATCH(launch_obs, ctx, O, ob);
+        CU(cudaGetLastError());
+        ++ctx->launches;
+    }
+    return 0;
+}
+
+int batch_impl(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, long long N, double* logL,
+               double* obs_state, uint32_t* status, uint32_t* newton_iters, double* traj) {
+    if (!ctx) return HMX_ERR_INVALID;
+    if (N < 0 || (N > 0 && !theta)) return fail(ctx, HMX_ERR_INVALID, "theta is NULL or N < 0");
+    if (!traj && !logL && N > 0) return fail(ctx, HMX_ERR_INVALID, "logL is NULL");
+    CU(cudaSetDevice(ctx->device));
+    ctx->last_evals = N;
+    CU(cudaMemsetAsync(ctx->d_counters + 1, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    if (N == 0) return 0;
+    const long long obs_stride = (long long)std::max(ctx->n_obs_max, 1) * 12;
+    const long long traj_stride = (long long)(ctx->cfg.n_steps + 1) * 12;
+    bool need_sync = false;
+    for (long long off = 0; off < N; off += kChunkEvals) {
+        const long long n = std::min(kChunkEvals, N - off);
+        int rc;
+        const void *d_theta, *d_cond;
+        void *d_logL, *d_obs, *d_status, *d_iters, *d_traj;
+        void *h_logL, *h_obs, *h_status, *h_iters, *h_traj;
+        if ((rc = stage_in(ctx, theta + off * HMX_NTHETA, (size_t)n * HMX_NTHETA * sizeof(double), ctx->theta, &d_theta))) return rc;
+        if ((rc = stage_in(ctx, cond_id ? cond_id + off : nullptr, (size_t)n * sizeof(int32_t), ctx->cond_id, &d_cond))) return rc;
+        if ((rc = stage_out(ctx, logL ? logL + off : nullptr, (size_t)n * sizeof(double), ctx->logL, &d_logL, &h_logL))) return rc;
+        if ((rc = stage_out(ctx, obs_state ? obs_state + off * obs_stride : nullptr, (size_t)n * obs_stride * sizeof(double),
+                            ctx->obs_state, &d_obs, &h_obs))) return rc;
+        if ((rc = stage_out(ctx, status ? status + off : nullptr, (size_t)n * sizeof(uint32_t), ctx->st_out0, &d_status, &h_status))) return rc;
+        if ((rc = stage_out(ctx, newton_iters ? newton_iters + off : nullptr, (size_t)n * sizeof(uint32_t), ctx->st_out1, &d_iters, &h_iters))) return rc;
+        if ((rc = stage_out(ctx, traj ? traj + off * traj_stride : nullptr, (size_t)n * traj_stride * sizeof(double), ctx->traj,
+                            &d_traj, &h_traj))) return rc;
+        if (!traj && !d_logL) return fail(ctx, HMX_ERR_INVALID, "logL is NULL");
+        if ((rc = run_chunk(ctx, (const double*)d_theta, (const int32_t*)d_cond, n, (double*)d_logL, (double*)d_obs,
+                            (uint32_t*)d_status, (uint32_t*)d_iters, (double*)d_traj, d_logL != nullptr))) return rc;
+        if (h_logL) CU(cudaMemcpyAsync(h_logL, d_logL, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (h_obs) CU(cudaMemcpyAsync(h_obs, d_obs, (size_t)n * obs_stride * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (h_status) CU(cudaMemcpyAsync(h_status, d_status, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (h_iters) CU(cudaMemcpyAsync(h_iters, d_iters, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (h_traj) CU(cudaMemcpyAsync(h_traj, d_traj, (size_t)n * traj_stride * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        const bool any_host = h_logL || h_obs || h_status || h_iters || h_traj;
+        need_sync = need_sync || any_host;
+        // staging buffers are reused by the next chunk: drain before overwriting them
+        if (off + kChunkEvals < N && (any_host || !is_device_ptr(theta))) CU(cudaStreamSynchronize(ctx->stream));
+    }
+    if (need_sync) CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hmx_abi_version(void) { return HMX_ABI_VERSION; }
+
+const char* hmx_last_error(const hmx_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int hmx_create(hmx_ctx** out, const hmx_config* cfg, int32_t device) {
+    hmx_ctx* ctx = nullptr;  // errors before allocation go to the thread-local message
+    if (!out) return fail(nullptr, HMX_ERR_INVALID, "ctx out-pointer is NULL");
+    *out = nullptr;
+    const char* why = "";
+    if (validate_config(cfg, &why) != 0) return fail(nullptr, HMX_ERR_INVALID, std::string("invalid config: ") + why);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return fail(nullptr, HMX_ERR_NO_DEVICE, "no CUDA device visible: libhamilton has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, HMX_ERR_INVALID, "device index out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, HMX_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail(nullptr, HMX_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                                     "; this library is built for sm_100a (B200) only");
+    ctx = new (std::nothrow) hmx_ctx();
+    if (!ctx) return fail(nullptr, HMX_ERR_OOM, "out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cfg = *cfg;
+    make_solver_consts(*cfg, ctx->K);
+    ctx->alpha = (cfg->alpha_const != 0.0);
+    ctx->hill = hill_variant(ctx->K);
+    for (int k = 0; k < cfg->n_cond; ++k) {
+        make_cond_consts(*cfg, k, ctx->C[k]);
+        memset(&ctx->oc[k], 0, sizeof(OdeCond));
+        for (int i = 0; i < 12; ++i) ctx->oc[k].g0[i] = ctx->C[k].g0[i];
+        for (int o = 0; o < HMX_MAX_OBS; ++o) ctx->oc[k].idx[o] = ctx->C[k].idx[o];
+        ctx->oc[k].n_obs = ctx->C[k].n_obs;
+        ctx->n_obs_max = std::max(ctx->n_obs_max, (int)ctx->C[k].n_obs);
+    }
+    for (int k = cfg->n_cond; k < HMX_MAX_COND; ++k) memset(&ctx->oc[k], 0, sizeof(OdeCond));
+
+#define CU_CREATE(call)                                                                                    \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) {                                                                           \
+            g_create_error = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            hmx_destroy(ctx);                                                                              \
+            return HMX_ERR_CUDA;                                                                           \
+        }                                                                                                  \
+    } while (0)
+    CU_CREATE(cudaSetDevice(device));
+    CU_CREATE(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    CU_CREATE(cudaMalloc((void**)&ctx->d_cond, sizeof(CondConsts) * HMX_MAX_COND));
+    CU_CREATE(cudaMemcpy(ctx->d_cond, ctx->C, sizeof(CondConsts) * HMX_MAX_COND, cudaMemcpyHostToDevice));
+    CU_CREATE(cudaMalloc((void**)&ctx->d_counters, 4 * sizeof(unsigned long long)));
+    CU_CREATE(cudaMemset(ctx->d_counters, 0, 4 * sizeof(unsigned long long)));
+    CU_CREATE(cudaMalloc((void**)&ctx->d_stage, sizeof(StageState)));
+    CU_CREATE(cudaMemset(ctx->d_stage, 0, sizeof(StageState)));
+    CU_CREATE(cudaMalloc((void**)&ctx->d_tickets, 64 * sizeof(unsigned int)));
+    CU_CREATE(cudaMemset(ctx->d_tickets, 0, 64 * sizeof(unsigned int)));
+    CU_CREATE(cudaMalloc((void**)&ctx->d_small, 4096 * sizeof(double)));
+    CU_CREATE(cudaEventCreate(&ctx->ev0));
+    CU_CREATE(cudaEventCreate(&ctx->ev1));
+    ctx->ode_blocks_per_sm = query_occupancy(ctx);
+    *out = ctx;
+    return HMX_OK;
+}
+
+void hmx_destroy(hmx_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->theta, &ctx->cond_id, &ctx->pairs, &ctx->status, &ctx->iters, &ctx->trips, &ctx->logL,
+                      &ctx->obs_state, &ctx->traj, &ctx->st_in0, &ctx->st_in1, &ctx->st_in2, &ctx->st_out0, &ctx->st_out1,
+                      &ctx->partial, &ctx->cs};
+    for (DevBuf* b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (ctx->d_cond) cudaFree(ctx->d_cond);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
+    if (ctx->d_tickets) cudaFree(ctx->d_tickets);
+    if (ctx->d_small) cudaFree(ctx->d_small);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int hmx_set_stream(hmx_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return HMX_ERR_INVALID;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return HMX_OK;
+}
+
+int hmx_synchronize(hmx_ctx* ctx) {
+    if (!ctx) return HMX_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return HMX_OK;
+}
+
+int hmx_loglik_batch(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, int64_t N, double* logL,
+                     double* obs_state, uint32_t* status, uint32_t* newton_iters) {
+    return batch_impl(ctx, theta, cond_id, N, logL, obs_state, status, newton_iters, nullptr);
+}
+
+int hmx_trajectory_batch(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, int64_t N, double* g,
+                         uint32_t* status, uint32_t* newton_iters) {
+    if (!ctx) return HMX_ERR_INVALID;
+    if (!g && N > 0) return fail(ctx, HMX_ERR_INVALID, "g is NULL");
+    return batch_impl(ctx, theta, cond_id, N, nullptr, nullptr, status, newton_iters, g);
+}
+
+int hmx_beta_step(hmx_ctx* ctx, const double* logL, int64_t N, double beta, double target_ess_ratio,
+                  double min_delta_beta, double max_delta_beta, double* delta_beta, double* ess_at_lo) {
+    if (!ctx) return HMX_ERR_INVALID;
+    if (N <= 0 || !logL || !delta_beta) return fail(ctx, HMX_ERR_INVALID, "hmx_beta_step: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    const void* d_l;
+    if ((rc = stage_in(ctx, logL, (size_t)N * sizeof(double), ctx->st_in0, &d_l))) return rc;
+    const int nb = red_blocks(N);
+    if ((rc = ensure(ctx, ctx->partial, (size_t)2 * kRedMaxBlocks * sizeof(double)))) return rc;
+    double* part = (double*)ctx->partial.p;
+    const bool out_dev = is_device_ptr(delta_beta);
+    double* d_db = out_dev ? delta_beta : ctx->d_small;
+    double* d_ess = ess_at_lo ? (is_device_ptr(ess_at_lo) ? ess_at_lo : ctx->d_small + 1) : nullptr;
+    max_kernel<<<nb, kRedThreads, 0, ctx->stream>>>((const double*)d_l, N, 1.0, part, ctx->d_stage);
+    bisect_init_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_stage, beta);
+    const double target = target_ess_ratio * (double)N;
+    for (int it = 0; it < 25; ++it)
+        bisect_step_kernel<<<nb, kRedThreads, 0, ctx->stream>>>((const double*)d_l, N, target, part, ctx->d_stage);
+    bisect_final_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_stage, beta, min_delta_beta, max_delta_beta, d_db, d_ess);
+    CU(cudaGetLastError());
+    ctx->launches += 28;
+    bool sync = false;
+    if (!out_dev) {
+        CU(cudaMemcpyAsync(delta_beta, d_db, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        sync = true;
+    }
+    if (ess_at_lo && !is_device_ptr(ess_at_lo)) {
+        CU(cudaMemcpyAsync(ess_at_lo, d_ess, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        sync = true;
+    }
+    if (sync) CU(cudaStreamSynchronize(ctx->stream));
+    return HMX_OK;
+}
+
+int hmx_weights(hmx_ctx* ctx, const double* logL, int64_t N, double delta_beta, double* w, double* log_Sj) {
+    if (!ctx) return HMX_ERR_INVALID;
+    if (N <= 0 || !logL || !w) return fail(ctx, HMX_ERR_INVALID, "hmx_weights: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    const void* d_l;
+    void *d_w, *h_w;
+    if ((rc = stage_in(ctx, logL, (size_t)N * sizeof(double), ctx->st_in0, &d_l))) return rc;
+    if ((rc = stage_out(ctx, w, (size_t)N * sizeof(double), ctx->st_out0, &d_w, &h_w))) return rc;
+    if ((rc = ensure(ctx, ctx->partial, (size_t)2 * kRedMaxBlocks * sizeof(double)))) return rc;
+    double* part = (double*)ctx->partial.p;
+    const int nb = red_blocks(N);
+    double* d_ls = log_Sj ? (is_device_ptr(log_Sj) ? log_Sj : ctx->d_small + 2) : nullptr;
+    max_kernel<<<nb, kRedThreads, 0, ctx->stream>>>((const double*)d_l, N, delta_beta, part, ctx->d_stage);
+    weights_exp_kernel<<<nb, kRedThreads, 0, ctx->stream>>>((const double*)d_l, N, delta_beta, (double*)d_w, part, ctx->d_stage);
+    weights_norm_kernel<<<nb, kRedThreads, 0, ctx->stream>>>((double*)d_w, N, ctx->d_stage, d_ls);
+    CU(cudaGetLastError());
+    ctx->launches += 3;
+    bool sync = false;
+    if (h_w) {
+        CU(cudaMemcpyAsync(h_w, d_w, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        sync = true;
+    }
+    if (log_Sj && !is_device_ptr(log_Sj)) {
+        CU(cudaMemcpyAsync(log_Sj, d_ls, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        sync = true;
+    }
+    if (sync) CU(cudaStreamSynchronize(ctx->stream));
+    return HMX_OK;
+}
+
+int hmx_resample(hmx_ctx* ctx, const double* w, int64_t N, double u, int64_t* idx) {
+    if (!ctx) return HMX_ERR_INVALID;
+    if (N <= 0 || !w || !idx) return fail(ctx, HMX_ERR_INVALID, "hmx_resample: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    const void* d_w;
+    void *d_idx, *h_idx;
+    if ((rc = stage_in(ctx, w, (size_t)N * sizeof(double), ctx->st_in0, &d_w))) return rc;
+    if ((rc = stage_out(ctx, idx, (size_t)N * sizeof(int64_t), ctx->st_out0, &d_idx, &h_idx))) return rc;
+    if ((rc = ensure(ctx, ctx->cs, (size_t)N * sizeof(double)))) return rc;
+    cumsum_serial_kernel<<<1, 32, 0, ctx->stream>>>((const double*)d_w, N, (double*)ctx->cs.p);
+    searchsorted_kernel<<<red_blocks(N), kRedThreads, 0, ctx->stream>>>((const double*)ctx->cs.p, N, u, (long long*)d_idx);
+    CU(cudaGetLastError());
+    ctx->launches += 2;
+    if (h_idx) {
+        CU(cudaMemcpyAsync(h_idx, d_idx, (size_t)N * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return HMX_OK;
+}
+
+static int moments_impl(hmx_ctx* ctx, const double* d_theta, const double* d_w, long long N, int d, double* d_mom) {
+    int rc;
+    const int nb = red_blocks(N);
+    if ((rc = ensure(ctx, ctx->partial, std::max((size_t)2 * kRedMaxBlocks, (size_t)(2 + d) * nb) * sizeof(double)))) return rc;
+    dim3 grid(nb, 2 + d);
+    wmoments_kernel<<<grid, kRedThreads, 0, ctx->stream>>>(d_theta, d_w, N, d, (double*)ctx->partial.p, d_mom, ctx->d_tickets);
+    CU(cudaGetLastError());
+    ++ctx->launches;
+    return 0;
+}
+
+static int scatter_impl(hmx_ctx* ctx, const double* d_theta, const double* d_w, long long N, int d, const double* d_mean,
+                        double* d_scatter) {
+    int rc;
+    const int nb = (int)std::max(1ll, std::min<long long>((N + kScatterChunk - 1) / kScatterChunk, 4ll * ctx->sm_count));
+    if ((rc = ensure(ctx, ctx->partial, std::max((size_t)2 * kRedMaxBlocks, (size_t)nb * d * d) * sizeof(double)))) return rc;
+    const size_t smem = (size_t)kScatterChunk * (d + 1) * sizeof(double);
+    wscatter_kernel<<<nb, kRedThreads, smem, ctx->stream>>>(d_theta, d_w, N, d, d_mean, (double*)ctx->partial.p, d_scatter,
+                                                            ctx->d_tickets + 40);
+    CU(cudaGetLastError());
+    ++ctx->launches;
+    return 0;
+}
+
+int hmx_weighted_moments(hmx_ctx* ctx, const double* theta, const double* w, int64_t N, int32_t d, double* moments) {
+    if (!ctx) return HMX_ERR_INVALID;
+    if (N <= 0 || !theta || !w || !moments || d < 1 || d > 32) return fail(ctx, HMX_ERR_INVALID, "hmx_weighted_moments: bad arguments (1 <= d <= 32)");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    const void *d_t, *d_w;
+    if ((rc = stage_in(ctx, theta, (size_t)N * d * sizeof(double), ctx->st_in1, &d_t))) return rc;
+    if ((rc = stage_in(ctx, w, (size_t)N * sizeof(double), ctx->st_in0, &d_w))) return rc;
+    const bool dev = is_device_ptr(moments);
+    double* d_m = dev ? moments : ctx->d_small + 8;
+    if ((rc = moments_impl(ctx, (const double*)d_t, (const double*)d_w, N, d, d_m))) return rc;
+    if (!dev) {
+        CU(cudaMemcpyAsync(moments, d_m, (size_t)(2 + d) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return HMX_OK;
+}
+
+int hmx_weighted_scatter(hmx_ctx* ctx, const double* theta, const double* w, int64_t N, int32_t d, const double* mean,
+                         double* scatter) {
+    if (!ctx) return HMX_ERR_INVALID;
+    if (N <= 0 || !theta || !w || !mean || !scatter || d < 1 || d > 32)
+        return fail(ctx, HMX_ERR_INVALID, "hmx_weighted_scatter: bad arguments (1 <= d <= 32)");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    const void *d_t, *d_w, *d_mean;
+    if ((rc = stage_in(ctx, theta, (size_t)N * d * sizeof(double), ctx->st_in1, &d_t))) return rc;
+    if ((rc = stage_in(ctx, w, (size_t)N * sizeof(double), ctx->st_in0, &d_w))) return rc;
+    if ((rc = stage_in(ctx, mean, (size_t)d * sizeof(double), ctx->st_in2, &d_mean))) return rc;
+    const bool dev = is_device_ptr(scatter);
+    double* d_s = dev ? scatter : ctx->d_small + 64;
+    if ((rc = scatter_impl(ctx, (const double*)d_t, (const double*)d_w, N, d, (const double*)d_mean, d_s))) return rc;
+    if (!dev) {
+        CU(cudaMemcpyAsync(scatter, d_s, (size_t)d * d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return HMX_OK;
+}
+
+int hmx_weighted_cov(hmx_ctx* ctx, const double* theta, const double* w, int64_t N, int32_t d, double* mean, double* cov) {
+    if (!ctx) return HMX_ERR_INVALID;
+    if (N <= 0 || !theta || !w || !cov || d < 1 || d > 32) return fail(ctx, HMX_ERR_INVALID, "hmx_weighted_cov: bad arguments (1 <= d <= 32)");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    const void *d_t, *d_w;
+    if ((rc = stage_in(ctx, theta, (size_t)N * d * sizeof(double), ctx->st_in1, &d_t))) return rc;
+    if ((rc = stage_in(ctx, w, (size_t)N * sizeof(double), ctx->st_in0, &d_w))) return rc;
+    double* d_mom = ctx->d_small + 8;      // [2+d]
+    double* d_mean = ctx->d_small + 48;    // [d]
+    double* d_scat = ctx->d_small + 1100;  // [d*d]
+    const bool cov_dev = is_device_ptr(cov);
+    double* d_cov = cov_dev ? cov : ctx->d_small + 2200;
+    const bool mean_dev = mean && is_device_ptr(mean);
+    double* d_mean_out = mean ? (mean_dev ? mean : ctx->d_small + 3300) : nullptr;
+    if ((rc = moments_impl(ctx, (const double*)d_t, (const double*)d_w, N, d, d_mom))) return rc;
+    wmean_kernel<<<1, 32, 0, ctx->stream>>>(d_mom, d, d_mean);
+    if ((rc = scatter_impl(ctx, (const double*)d_t, (const double*)d_w, N, d, d_mean, d_scat))) return rc;
+    wcov_final_kernel<<<1, 256, 0, ctx->stream>>>(d_mom, d_scat, d, d_cov, d_mean_out, d_mean);
+    CU(cudaGetLastError());
+    ctx->launches += 2;
+    bool sync = false;
+    if (!cov_dev) {
+        CU(cudaMemcpyAsync(cov, d_cov, (size_t)d * d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        sync = true;
+    }
+    if (mean && !mean_dev) {
+        CU(cudaMemcpyAsync(mean, d_mean_out, (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        sync = true;
+    }
+    if (sync) CU(cudaStreamSynchronize(ctx->stream));
+    return HMX_OK;
+}
+
+int hmx_set_timing(hmx_ctx* ctx, int32_t enabled) {
+    if (!ctx) return HMX_ERR_INVALID;
+    ctx->timing = enabled != 0;
+    return HMX_OK;
+}
+
+int hmx_get_counters(hmx_ctx* ctx, hmx_counters* out) {
+    if (!ctx || !out) return HMX_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    unsigned long long h[4] = {0, 0, 0, 0};
+    CU(cudaMemcpy(h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    if (ctx->timing_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ode_ms = ms;
+        else cudaGetLastError();
+        ctx->timing_pending = false;
+    }
+    out->evals = ctx->last_evals;
+    out->newton_iters = (int64_t)h[1];
+    out->q_evals = (int64_t)h[2];
+    out->kernel_launches = ctx->launches;
+    out->last_ode_kernel_ms = ctx->last_ode_ms;
+    return HMX_OK;
+}
+
+int hmx_measure_fp64_peak(hmx_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return HMX_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU(cudaEventRecord(a, ctx->stream));
+        fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->d_small, iters, 0.999999, 1e-6);
+        CU(cudaEventRecord(b, ctx->stream));
+        CU(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, a, b));
+        const double flops = 2.0 * (double)blocks * threads * (double)iters * kPeakFmaPerIter;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    ctx->launches += 4;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *tflops = best;
+    return HMX_OK;
+}
+
+}  // extern "C"

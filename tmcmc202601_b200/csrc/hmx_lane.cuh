@@ -1,0 +1,167 @@
+// hmx_lane.cuh -- per-lane state machine of the batched implicit integrator.
+//
+// The reference advances one particle at a time: for each of n_steps time steps run <= max_newton_iter
+// damped quasi-Newton iterations, each with a backtracking line search (S5:291-432, 837-882).  Iteration
+// and trial counts are data dependent (2-50 iterations per step, 1-14 trials per iteration), so running
+// 32 particles of a warp in lock-step over (time step, iteration, trial) would idle most lanes.
+//
+// Here every lane carries its own (time step, iteration, line-search) position and all lanes of a warp
+// execute the same "trip":   candidate -> residual -> accept/reject decision -> [direction solve].
+// A lane that converges simply starts its next time step on the next trip; a lane that finishes its
+// particle fetches the next one from a global work counter.  Divergence is limited to the predicated
+// direction solve and the (rare) step-advance bookkeeping.
+//
+// Iterate semantics reproduced from the reference ("same iterate sequence"):
+//   * phi, psi are clipped to [1e-12, 1-1e-12] and WRITTEN BACK to the iterate at the start of every
+//     iteration; phi_0 is clipped only inside Q/K; gamma is never clipped            (S5:66-79, 337-340)
+//   * NaN residual at an iteration start ends the Newton loop with the current iterate (S5:342-348)
+//   * the first step length in {1, 1/2, ...} (> 1e-4) with ||Q_trial||_inf < ||Q||_inf is accepted and
+//     the accepted trial is NOT clipped                                               (S5:381-425)
+//   * if no trial improves, the full step is taken and the old norm is kept           (S5:427-428)
+//   * the loop stops when ||Q||_inf < eps (1 + 10 t_{n+1}) or after max_newton_iter   (S5:430-431, 861)
+#pragma once
+
+#include "hmx_model.cuh"
+
+namespace hmx {
+
+enum : int32_t { kModeEval = 0, kModeTrial = 1 };
+
+constexpr uint32_t kStNonfinite = 1u, kStMaxIter = 2u, kStSingular = 4u;  // == HMX_ST_* in include/hmx.h
+
+struct Lane {
+    double gp[11];   // previous time level: phi(5), phi_0, psi(5)
+    double g[12];    // current Newton iterate
+    double d[12];    // current Newton direction
+    double A[15];    // packed symmetric interaction matrix
+    double b[5];     // decay vector (only read when alpha != 0)
+    double normQ;    // ||Q||_inf at the iterate
+    double step;     // current line-search step length
+    double tol;      // eps (1 + 10 t_{n+1})
+    int32_t step_idx;  // time level of gp
+    int32_t it;        // directions computed in this time step
+    int32_t mode;
+    uint32_t status;
+    uint32_t iters;  // total directions (quasi-Newton iterations)
+    uint32_t trips;  // total residual evaluations
+};
+
+HMX_HD double step_tol(const SolverConsts& K, int32_t step_idx) {
+    const double tt = (double)(step_idx + 1) * K.dt;  // S5:860-861
+    return K.eps * (1.0 + 10.0 * tt);
+}
+
+// g0 = [phi_init, 1 - sum(phi_init), 0.999 x5, 0]  (S5:564-576)
+HMX_HD void lane_init(const SolverConsts& K, Lane& s, const double* theta, const double* g0) {
+    theta_to_Ab(theta, s.A, s.b);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s.g[i] = g0[i];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) s.gp[i] = g0[i];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s.d[i] = 0.0;
+    s.normQ = 0.0;
+    s.step = 1.0;
+    s.step_idx = 0;
+    s.it = 0;
+    s.mode = kModeEval;
+    s.status = 0u;
+    s.iters = 0u;
+    s.trips = 0u;
+    s.tol = step_tol(K, 0);
+}
+
+// One trip.  Returns true when the Newton loop of the current time step has ended; s.g then holds
+// g_arr[step_idx + 1] and the caller must call lane_advance().
+template <bool ALPHA, int HILL>
+HMX_HD bool lane_trip(const SolverConsts& K, Lane& s) {
+    double x[12];
+    const bool trial = (s.mode == kModeTrial);
+    const double sl = trial ? s.step : 0.0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) x[i] = trial ? fma(sl, s.d[i], s.g[i]) : s.g[i];
+
+    Eval e;
+    residual<ALPHA, HILL>(K, x, s.gp, s.A, s.b, e);
+    ++s.trips;
+
+    bool need_dir = false, finished = false, take_clipped = false, take_raw = false, nan_break = false;
+    if (!trial) {
+        take_clipped = true;  // write-back of the clipped phi/psi
+        if (e.nan) {
+            finished = true;
+            nan_break = true;
+        } else {
+            s.normQ = e.norm;
+            need_dir = true;
+        }
+    } else {
+        const bool accept = (!e.nan) && (e.norm < s.normQ);
+        if (accept) {
+            s.normQ = e.norm;
+            if (s.normQ < s.tol || s.it >= K.max_iter) {
+                take_raw = true;  // the accepted trial leaves the Newton loop unclipped
+                finished = true;
+            } else {
+                take_clipped = true;  // next iteration: same residual, clipped write-back
+                need_dir = true;
+            }
+        } else {
+            s.step *= 0.5;
+            if (!(s.step > 1e-4)) {
+                // no improving step length: full step, keep the old norm
+#pragma unroll
+                for (int i = 0; i < 12; ++i) s.g[i] = s.g[i] + s.d[i];
+                if (s.normQ < s.tol || s.it >= K.max_iter) {
+                    finished = true;
+                } else {
+                    s.mode = kModeEval;
+                }
+            }
+        }
+    }
+    if (take_raw) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) s.g[i] = x[i];
+    }
+    if (take_clipped) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            s.g[i] = e.ph[i];
+            s.g[6 + i] = e.ps[i];
+        }
+        s.g[5] = x[5];
+        s.g[11] = x[11];
+    }
+    if (need_dir) {
+        direction<ALPHA, HILL>(K, e, s.A, s.b, s.d);
+        double chk = 0.0;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) chk = fma(s.d[i], 0.0, chk);
+        if (chk != 0.0) s.status |= kStSingular;  // inf/NaN direction
+        ++s.it;
+        ++s.iters;
+        s.step = 1.0;
+        s.mode = kModeTrial;
+    }
+    if (finished && !nan_break && !(s.normQ < s.tol)) s.status |= kStMaxIter;  // range(max_newton_iter) exhausted
+    return finished;
+}
+
+// Bookkeeping after a finished time step: s.g becomes the new previous level.
+// Returns true when all n_steps levels are done.
+HMX_HD bool lane_advance(const SolverConsts& K, Lane& s) {
+    double chk = 0.0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) chk = fma(s.g[i], 0.0, chk);
+    if (chk != 0.0) s.status |= kStNonfinite;  // EV:657-667 scans the whole trajectory
+#pragma unroll
+    for (int i = 0; i < 11; ++i) s.gp[i] = s.g[i];
+    ++s.step_idx;
+    s.it = 0;
+    s.mode = kModeEval;
+    s.tol = step_tol(K, s.step_idx);
+    return s.step_idx >= K.n_steps;
+}
+
+}  // namespace hmx

@@ -1,0 +1,388 @@
+// hmx_model.cuh -- arithmetic of one implicit time step of the 5-species Hamilton ODE, written for
+// one CUDA thread per (particle, condition) solve with every live quantity in registers.
+//
+// What the reference computes per quasi-Newton iteration (S5 = tmcmc/program2602/improved_5species_jit.py):
+//   residual Q(g_new; g_prev)            S5:43-127
+//   approximate Jacobian K (12x12)       S5:129-289   (NOT the exact derivative -- reproduced as is)
+//   delta = solve(K, -Q)  (LAPACK dgesv) S5:369-373
+//   backtracking on ||Q||_inf            S5:381-431
+//
+// B200-first restructuring (same mathematics, different algorithm; parity is checked against the
+// dense oracle in tests/):
+//   * K is never formed.  With unknowns ordered per species (dphi_i, dpsi_i), the 10x10 (phi,psi) part is
+//       M = blockdiag(D_i) + P C Q^T,   P = blockdiag([psi_i; phi_i]),  Q = blockdiag([psi_i, phi_i]),
+//     because every A-derived off-diagonal 2x2 block of S5:197-245 is the rank-one outer product
+//     -c/eta_i * h_i * A_ij * [psi_i; phi_i] [psi_j, phi_j]   (Hill corrections S5:249-287 included: they
+//     scale row-species 4 by h and add a multiple of the same outer product at block (4,3)).
+//     The phi_0 row (S5:222-223) and the constraint row / gamma column (S5:220,247) are eliminated
+//     analytically.  What remains is five 2x2 inverses, ONE 5x5 pivoted solve with two right-hand sides
+//     and a scalar closure for d-gamma: ~0.9 kflop instead of ~2.4 kflop for K + dgesv, and ~60 live
+//     doubles instead of 144+, which is what lets the whole step stay in registers.
+//   * all barrier terms of one variable v share ONE reciprocal r = 1/(v(v-1)):
+//       Kp1(2-4v)/((v-1)^3 v^3) = -2Kp1(2v-1) r^3      (phi, phi_0 rows AND, after combining its two
+//                                                         fractions, the psi rows S5:117-119)
+//       phi_p (S5:185-187)      = 2Kp1(2v-1) r^3 (2 + 3(2v-1) r)
+//       psi_p (S5:189)          = 4Kp1(3 + 5 v(v-1)) r^4
+//   * the residual of an accepted line-search trial IS the residual the next iteration would recompute
+//     (same clipped inputs), so each state-machine trip evaluates Q exactly once.
+//
+// Everything here is __host__ __device__ so tests can run the identical arithmetic on the CPU
+// (tests/csrc/host_emulation.cpp); the shipped library only instantiates the device side.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define HMX_HD __host__ __device__ __forceinline__
+#else
+#define HMX_HD inline
+#endif
+
+namespace hmx {
+
+constexpr double kClipLo = 1e-12;         // S5:64
+constexpr double kClipHi = 1.0 - 1e-12;   // S5:68
+
+// Solver constants shared by all evaluations of a context (lives in __constant__ memory on the device).
+struct SolverConsts {
+    double dt, inv_dt, eps, Kp1, c, alpha, K_hill, n_hill, Kn;  // Kn = K_hill^n_hill
+    double eta[5], eta_phi[5], inv_eta[5], c_eta[5], alpha_eta[5];  // c/eta_i, alpha/eta_i
+    int32_t n_steps, max_iter;
+    int32_t hill_mode;  // 0 off, 1..4 integer exponent, 5 generic pow
+    int32_t pad_;
+};
+
+HMX_HD double clip01(double v) {
+    // two ordered compares: NaN stays NaN exactly like S5:66-69
+    return (v < kClipLo) ? kClipLo : ((v > kClipHi) ? kClipHi : v);
+}
+
+// packed symmetric A: index of (i,j)
+HMX_HD constexpr int apk(int i, int j) {
+    return (i <= j) ? (i * 5 - (i * (i - 1)) / 2 + (j - i)) : (j * 5 - (j * (j - 1)) / 2 + (i - j));
+}
+
+// theta (20) -> packed symmetric A (15) and b (5): S5:513-559
+HMX_HD void theta_to_Ab(const double* th, double (&A)[15], double (&b)[5]) {
+#pragma unroll
+    for (int k = 0; k < 15; ++k) A[k] = 0.0;
+    A[apk(0, 0)] = th[0];
+    A[apk(0, 1)] = th[1];
+    A[apk(1, 1)] = th[2];
+    b[0] = th[3];
+    b[1] = th[4];
+    A[apk(2, 2)] = th[5];
+    A[apk(2, 3)] = th[6];
+    A[apk(3, 3)] = th[7];
+    b[2] = th[8];
+    b[3] = th[9];
+    A[apk(0, 2)] = th[10];
+    A[apk(0, 3)] = th[11];
+    A[apk(1, 2)] = th[12];
+    A[apk(1, 3)] = th[13];
+    A[apk(4, 4)] = th[14];
+    b[4] = th[15];
+    A[apk(0, 4)] = th[16];
+    A[apk(1, 4)] = th[17];
+    A[apk(2, 4)] = th[18];
+    A[apk(3, 4)] = th[19];
+}
+
+// x^n and x^(n-1) for the Hill gate (S5:92, 278); integer exponents avoid pow()
+template <int HILL>
+HMX_HD void hill_powers(const SolverConsts& K, double x, double& xn, double& xn1) {
+    if (HILL == 2) {
+        xn = pow(x, K.n_hill);
+        xn1 = pow(x, K.n_hill - 1.0);
+    } else {
+        const double x2 = x * x;
+        switch (K.hill_mode) {
+            case 1: xn = x; xn1 = 1.0; break;
+            case 2: xn = x2; xn1 = x; break;
+            case 3: xn = x2 * x; xn1 = x2; break;
+            default: xn = x2 * x2; xn1 = x2 * x; break;
+        }
+    }
+}
+
+// Everything one residual evaluation produces that the direction solve reuses.
+struct Eval {
+    double ph[5], ps[5], ph0;      // clipped values the residual was evaluated at
+    double rph[5], rps[5];         // 1/(v(v-1))
+    double fph[5], fps[5];         // barrier value  -2Kp1(2v-1) r^3
+    double f0, r0;                 // same for phi_0
+    double p[5];                   // phi_i psi_i
+    double I[5];                   // gated interaction (A p)_i * h_i
+    double Iraw4, h, dh_dx;        // Hill gate state (h = 1 when the gate is off)
+    double phd[5], psd[5];         // time derivatives
+    double Q[12];
+    double norm;                   // ||Q||_inf
+    bool nan;                      // any(isnan(Q))
+};
+
+// Residual Q at the candidate x (S5:43-127).  gp = [phi_old(5), phi0_old, psi_old(5)].
+template <bool ALPHA, int HILL>
+HMX_HD void residual(const SolverConsts& K, const double (&x)[12], const double (&gp)[11],
+                     const double (&A)[15], const double (&b)[5], Eval& e) {
+    const double gam = x[11];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        e.ph[i] = clip01(x[i]);
+        e.ps[i] = clip01(x[6 + i]);
+    }
+    e.ph0 = clip01(x[5]);
+    const double m2K = -2.0 * K.Kp1;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const double v = e.ph[i], u = e.ps[i];
+        const double rv = 1.0 / fma(v, v, -v), ru = 1.0 / fma(u, u, -u);
+        e.rph[i] = rv;
+        e.rps[i] = ru;
+        e.fph[i] = (m2K * fma(2.0, v, -1.0)) * (rv * rv * rv);
+        e.fps[i] = (m2K * fma(2.0, u, -1.0)) * (ru * ru * ru);
+        e.p[i] = v * u;
+        e.phd[i] = (v - gp[i]) * K.inv_dt;
+        e.psd[i] = (u - gp[6 + i]) * K.inv_dt;
+    }
+    {
+        const double v = e.ph0;
+        e.r0 = 1.0 / fma(v, v, -v);
+        e.f0 = (m2K * fma(2.0, v, -1.0)) * (e.r0 * e.r0 * e.r0);
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        double s = A[apk(i, 0)] * e.p[0];
+#pragma unroll
+        for (int j = 1; j < 5; ++j) s = fma(A[apk(i, j)], e.p[j], s);
+        e.I[i] = s;
+    }
+    e.h = 1.0;
+    e.dh_dx = 0.0;
+    e.Iraw4 = e.I[4];
+    if (HILL != 0) {
+        const double fn = e.p[3];
+        if (fn > 1e-20) {
+            double xn, xn1;
+            hill_powers<HILL>(K, fn, xn, xn1);
+            const double rden = 1.0 / (K.Kn + xn);
+            e.h = xn * rden;
+            e.dh_dx = K.n_hill * K.Kn * xn1 * (rden * rden);
+        } else {
+            e.h = 0.0;
+        }
+        e.I[4] *= e.h;
+    }
+    double nrm = 0.0, asum = 0.0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const double v = e.ph[i], u = e.ps[i];
+        // Q_i, S5:98-106
+        const double t2 = K.inv_eta[i] * (gam + fma(fma(K.eta[i] * u, u, K.eta_phi[i]), e.phd[i],
+                                                     K.eta[i] * e.p[i] * e.psd[i]));
+        const double qi = e.fph[i] + t2 - K.c_eta[i] * u * e.I[i];
+        // Q_{6+i}, S5:116-123
+        double qs = e.fps[i] + fma(e.p[i], e.phd[i], v * v * e.psd[i]) - K.c_eta[i] * v * e.I[i];
+        if (ALPHA) qs += (b[i] * K.alpha_eta[i]) * u;
+        e.Q[i] = qi;
+        e.Q[6 + i] = qs;
+        nrm = fmax(nrm, fmax(fabs(qi), fabs(qs)));
+        asum += fabs(qi) + fabs(qs);
+    }
+    e.Q[5] = gam + e.f0 + (e.ph0 - gp[5]) * K.inv_dt;                              // S5:109-113
+    e.Q[11] = ((((e.ph[0] + e.ph[1]) + e.ph[2]) + e.ph[3]) + e.ph[4]) + e.ph0 - 1.0;  // S5:126
+    nrm = fmax(nrm, fmax(fabs(e.Q[5]), fabs(e.Q[11])));
+    asum += fabs(e.Q[5]) + fabs(e.Q[11]);
+    e.norm = nrm;
+    e.nan = (asum != asum);  // true for NaN only (a sum of |.| is +inf, not NaN, for infinite entries): S5:342-348
+}
+
+// 5x5 solve with two right-hand sides.  S[r][0..4] matrix, S[r][5], S[r][6] the two right-hand sides ->
+// overwritten with the solutions.
+//
+// The matrix is S = I + diag(g) C with g_i = q_i^T D_i^{-1} p_i ~ dt and |C_ij| = c/eta |A_ij|, i.e. a small
+// perturbation of the identity for every physically meaningful input (|g C| ~ 0.07 at the production MAP).
+// Fast path: elimination in natural order, fully unrolled, registers only.  It reports the smallest pivot
+// magnitude; when that drops below kPivotFloor the caller redoes the solve with partial pivoting
+// (solve5x2_pivoted, local memory, dynamic indexing -- off the hot path).
+constexpr double kPivotFloor = 0.0625;
+
+HMX_HD double solve5x2_natural(double (&S)[5][7]) {
+    double rp[5];
+    double pmin = 1e300;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        pmin = fmin(pmin, fabs(S[k][k]));
+        rp[k] = 1.0 / S[k][k];
+#pragma unroll
+        for (int r = k + 1; r < 5; ++r) {
+            const double l = S[r][k] * rp[k];
+#pragma unroll
+            for (int cc = k + 1; cc < 7; ++cc) S[r][cc] = fma(-l, S[k][cc], S[r][cc]);
+        }
+    }
+#pragma unroll
+    for (int k = 4; k >= 0; --k) {
+        double s0 = S[k][5], s1 = S[k][6];
+#pragma unroll
+        for (int cc = k + 1; cc < 5; ++cc) {
+            s0 = fma(-S[k][cc], S[cc][5], s0);
+            s1 = fma(-S[k][cc], S[cc][6], s1);
+        }
+        S[k][5] = s0 * rp[k];
+        S[k][6] = s1 * rp[k];
+    }
+    return pmin;  // NaN-safe: fmin ignores NaN pivots, the caller also checks the direction for finiteness
+}
+
+// Partial (row) pivoting variant for the rare ill-scaled case.  M is the untouched copy of the system.
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#endif
+static void solve5x2_pivoted(const double* M /*[35]*/, double* X /*[10]: x0[5], x1[5]*/) {
+    double T[5][7];
+    for (int r = 0; r < 5; ++r)
+        for (int cc = 0; cc < 7; ++cc) T[r][cc] = M[r * 7 + cc];
+    for (int k = 0; k < 5; ++k) {
+        int p = k;
+        double best = fabs(T[k][k]);
+        for (int r = k + 1; r < 5; ++r) {
+            const double a = fabs(T[r][k]);
+            if (a > best) {
+                best = a;
+                p = r;
+            }
+        }
+        if (p != k)
+            for (int cc = 0; cc < 7; ++cc) {
+                const double t = T[k][cc];
+                T[k][cc] = T[p][cc];
+                T[p][cc] = t;
+            }
+        const double rpk = 1.0 / T[k][k];
+        for (int r = k + 1; r < 5; ++r) {
+            const double l = T[r][k] * rpk;
+            for (int cc = k + 1; cc < 7; ++cc) T[r][cc] = fma(-l, T[k][cc], T[r][cc]);
+        }
+    }
+    for (int k = 4; k >= 0; --k) {
+        double s0 = T[k][5], s1 = T[k][6];
+        for (int cc = k + 1; cc < 5; ++cc) {
+            s0 = fma(-T[k][cc], X[cc], s0);
+            s1 = fma(-T[k][cc], X[5 + cc], s1);
+        }
+        X[k] = s0 / T[k][k];
+        X[5 + k] = s1 / T[k][k];
+    }
+}
+
+// Quasi-Newton direction delta = solve(K, -Q) with K the reference's approximate Jacobian (S5:129-289)
+// evaluated at the point of `e`, computed through the block structure described at the top.
+template <bool ALPHA, int HILL>
+HMX_HD void direction(const SolverConsts& K, const Eval& e, const double (&A)[15], const double (&b)[5],
+                      double (&delta)[12]) {
+    double a0[5], a1[5], b0[5], b1[5], d0[5], d1[5];  // D_i^{-1} r_i, D_i^{-1} u_i, D_i^{-1} [psi;phi]
+    double S[5][7];
+    double hrow[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) hrow[i] = 1.0;
+    if (HILL != 0) hrow[4] = e.h;  // h == 1 reproduces "no correction" (S5:250)
+
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const double v = e.ph[i], u = e.ps[i], pd = e.phd[i], sd = e.psd[i];
+        const double ce = K.c_eta[i], eta = K.eta[i];
+        const double sv = fma(2.0, v, -1.0);
+        const double phi_p = -e.fph[i] * fma(3.0 * sv, e.rph[i], 2.0);                                  // S5:185-187
+        const double wu = fma(u, u, -u);
+        const double r2 = e.rps[i] * e.rps[i];
+        const double psi_p = (4.0 * K.Kp1) * fma(5.0, wu, 3.0) * (r2 * r2);                              // S5:189
+        const double aii = hrow[i] * A[apk(i, i)];
+        const double ap = aii * e.p[i];
+        // 2x2 diagonal block of species i (rows i, 6+i; columns i, 6+i), S5:199-245 (+ S5:254-271)
+        const double d00 = phi_p + K.inv_eta[i] * fma(fma(eta * u, u, K.eta_phi[i]), K.inv_dt, eta * u * sd) -
+                           ce * u * fma(2.0 * aii, u, e.I[i]);
+        const double d01 = K.inv_eta[i] * (eta * fma(2.0 * u, pd, fma(v, sd, e.p[i] * K.inv_dt))) -
+                           ce * fma(3.0, ap, e.I[i]);
+        const double d10 = fma(u, pd, fma(e.p[i], K.inv_dt, 2.0 * v * sd)) - ce * fma(3.0, ap, 2.0 * e.I[i]);
+        double d11 = psi_p + fma(v, pd, v * v * K.inv_dt) - 2.0 * ce * aii * v * v;
+        if (ALPHA) d11 += b[i] * K.alpha_eta[i];
+        // inverse by Cramer with an fma-compensated determinant
+        const double t = d01 * d10;
+        const double det = fma(d00, d11, -t) + fma(-d01, d10, t);
+        const double rdet = 1.0 / det;
+        const double r0 = -e.Q[i], r1 = -e.Q[6 + i];
+        a0[i] = fma(d11, r0, -d01 * r1) * rdet;
+        a1[i] = fma(d00, r1, -d10 * r0) * rdet;
+        b0[i] = (d11 * K.inv_eta[i]) * rdet;  // u_i = (1/eta_i, 0): S5:220
+        b1[i] = (-d10 * K.inv_eta[i]) * rdet;
+        d0[i] = fma(d11, u, -d01 * v) * rdet;
+        d1[i] = fma(d00, v, -d10 * u) * rdet;
+    }
+    // off-diagonal coefficients C_ij = -c/eta_i h_i A_ij (+ the dh/dx outer product at (4,3), S5:273-287)
+    double Cm[5][5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const double s = -K.c_eta[i] * hrow[i];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) Cm[i][j] = (i == j) ? 0.0 : s * A[apk(i, j)];
+    }
+    if (HILL != 0) {
+        if (e.h < 1.0) Cm[4][3] = fma(-K.c_eta[4] * e.Iraw4, e.dh_dx, Cm[4][3]);
+    }
+    auto build_S = [&](double (&T)[5][7]) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const double gi = fma(e.ps[i], d0[i], e.ph[i] * d1[i]);  // q_i^T D_i^{-1} p_i
+#pragma unroll
+            for (int j = 0; j < 5; ++j) T[i][j] = (i == j) ? 1.0 : gi * Cm[i][j];
+            T[i][5] = fma(e.ps[i], a0[i], e.ph[i] * a1[i]);
+            T[i][6] = fma(e.ps[i], b0[i], e.ph[i] * b1[i]);
+        }
+    };
+    build_S(S);
+    if (!(solve5x2_natural(S) >= kPivotFloor)) {  // rare: rebuild and redo with row pivoting
+        double T[5][7], X[10];
+        build_S(T);
+        solve5x2_pivoted(&T[0][0], X);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            S[i][5] = X[i];
+            S[i][6] = X[5 + i];
+        }
+    }
+    // phi_0 row and the constraint row: S5:222-223, 247
+    const double s0v = fma(2.0, e.ph0, -1.0);
+    const double K55 = -e.f0 * fma(3.0 * s0v, e.r0, 2.0) + K.inv_dt;
+    const double rK55 = 1.0 / K55;
+    double sumY1 = 0.0, sumY2 = 0.0;
+    double y10[5], y11[5], y20[5], y21[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            if (j != i) {
+                t1 = fma(Cm[i][j], S[j][5], t1);
+                t2 = fma(Cm[i][j], S[j][6], t2);
+            }
+        }
+        y10[i] = fma(-d0[i], t1, a0[i]);
+        y11[i] = fma(-d1[i], t1, a1[i]);
+        y20[i] = fma(-d0[i], t2, b0[i]);
+        y21[i] = fma(-d1[i], t2, b1[i]);
+        sumY1 += y10[i];
+        sumY2 += y20[i];
+    }
+    const double srhs = fma(e.Q[5], rK55, -e.Q[11]);
+    const double dgam = (sumY1 - srhs) / (sumY2 + rK55);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        delta[i] = fma(-dgam, y20[i], y10[i]);
+        delta[6 + i] = fma(-dgam, y21[i], y11[i]);
+    }
+    delta[5] = (-e.Q[5] - dgam) * rK55;
+    delta[11] = dgam;
+}
+
+}  // namespace hmx

@@ -1,0 +1,296 @@
+// hmx_stage.cuh -- per-stage TMCMC arithmetic on the device (K2-K5 of SURVEY.md section 2.3).
+//
+// All reductions are deterministic: every block writes its partial to a fixed slot and the block that
+// draws the last ticket adds the slots in index order, so replicas on different GPUs that received the
+// same log-likelihood vector (NCCL all-gather) take bit-identical decisions.
+//
+//   K2 beta_bisect_*   25-step bisection on ESS(delta) >= ratio*N                         (TM:613-659)
+//   K3 weights_*       w = exp(d*logL - max), sum, normalise, log S_j                      (TM:686-701)
+//   K4 cumsum_serial   np.cumsum semantics (strict left-to-right adds) + searchsorted      (TM:186-198)
+//   K5 wcov_*          np.cov(theta.T, aweights=w), as moments + centred scatter           (TM:766)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hmx {
+
+constexpr int kRedThreads = 256;
+constexpr int kRedMaxBlocks = 1024;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// block-wide sum / max of one value per thread (blockDim.x == kRedThreads); result valid in thread 0
+template <bool IS_MAX>
+__device__ __forceinline__ double block_reduce(double v, double* sm /*[8]*/) {
+    v = IS_MAX ? warp_max(v) : warp_sum(v);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sm[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        v = (lane < (kRedThreads >> 5)) ? sm[lane] : (IS_MAX ? -INFINITY : 0.0);
+        v = IS_MAX ? warp_max(v) : warp_sum(v);
+    }
+    return v;
+}
+
+// returns true in thread 0 of the block that finished last
+__device__ __forceinline__ bool last_block(unsigned int* ticket) {
+    __shared__ bool is_last;
+    __threadfence();   // publish this thread's partial(s)
+    __syncthreads();   // ... for every thread of the block, before the ticket is drawn
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+        if (is_last) *ticket = 0u;  // re-arm for the next launch on this stream
+    }
+    __syncthreads();
+    return is_last;
+}
+
+// ---- state shared by the stage kernels (device memory, owned by the context) ----------------------------
+struct StageState {
+    double vmax;          // max(logL) or max(delta*logL)
+    double lo, hi;        // bisection bracket
+    double ess_lo;        // ESS at the last accepted mid (NaN if none)
+    double sum_w, sum_w2;
+    double delta_beta;    // result of K2
+    double log_Sj;        // result of K3
+    int32_t uniform_fallback;
+    unsigned int ticket;
+};
+
+// max over x[i]*scale (scale = 1 for K2, delta for K3: the reference maxes the scaled vector, TM:619,687)
+__global__ void __launch_bounds__(kRedThreads) max_kernel(const double* __restrict__ x, long long N, double scale,
+                                                          double* partial, StageState* st) {
+    __shared__ double sm[8];
+    double m = -INFINITY;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
+        m = fmax(m, x[i] * scale);
+    m = block_reduce<true>(m, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = m;
+    if (last_block(&st->ticket)) {
+        double v = -INFINITY;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) v = fmax(v, __ldcg(partial + b));
+        v = block_reduce<true>(v, sm);
+        if (threadIdx.x == 0) st->vmax = v;
+    }
+}
+
+__global__ void bisect_init_kernel(StageState* st, double beta) {
+    st->lo = 0.0;
+    st->hi = 1.0 - beta;
+    st->ess_lo = nan("");
+}
+
+// one bisection step: ESS(mid) = (sum w)^2 / sum w^2 with w = exp(mid (logL - max))   (TM:618-650)
+__global__ void __launch_bounds__(kRedThreads) bisect_step_kernel(const double* __restrict__ logL, long long N,
+                                                                   double target, double* partial, StageState* st) {
+    __shared__ double sm[8];
+    const double mid = 0.5 * (st->lo + st->hi);
+    const double vmax = st->vmax;
+    double s1 = 0.0, s2 = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const double w = exp(mid * (logL[i] - vmax));
+        s1 += w;
+        s2 = fma(w, w, s2);
+    }
+    s1 = block_reduce<false>(s1, sm);
+    s2 = block_reduce<false>(s2, sm);
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = s1;
+        partial[2 * blockIdx.x + 1] = s2;
+    }
+    if (last_block(&st->ticket)) {
+        double a = 0.0, b = 0.0;
+        for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) {
+            a += __ldcg(partial + 2 * k);
+            b += __ldcg(partial + 2 * k + 1);
+        }
+        a = block_reduce<false>(a, sm);
+        b = block_reduce<false>(b, sm);
+        if (threadIdx.x == 0) {
+            const double ess = (a > 0.0) ? (a * a) / b : 0.0;  // sum_w <= 0 -> ess = 0 (TM:622-623)
+            if (ess >= target) {
+                st->lo = mid;
+                st->ess_lo = ess;
+            } else {
+                st->hi = mid;
+            }
+        }
+    }
+}
+
+__global__ void bisect_final_kernel(StageState* st, double beta, double min_db, double max_db, double* out_db,
+                                    double* out_ess) {
+    // TM:656-657
+    const double raw = fmax(st->lo, min_db);
+    const double db = fmin(fmin(raw, max_db), 1.0 - beta);
+    st->delta_beta = db;
+    if (out_db) *out_db = db;
+    if (out_ess) *out_ess = st->ess_lo;
+}
+
+// K3: w_i = exp(delta logL_i - max);  partial sums
+__global__ void __launch_bounds__(kRedThreads) weights_exp_kernel(const double* __restrict__ logL, long long N, double delta,
+                                                                   double* __restrict__ w, double* partial, StageState* st) {
+    __shared__ double sm[8];
+    const double vmax = st->vmax;
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const double v = exp(__dsub_rn(__dmul_rn(delta, logL[i]), vmax));  // product rounded first, as NumPy does
+        w[i] = v;
+        s += v;
+    }
+    s = block_reduce<false>(s, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    if (last_block(&st->ticket)) {
+        double a = 0.0;
+        for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) a += __ldcg(partial + k);
+        a = block_reduce<false>(a, sm);
+        if (threadIdx.x == 0) {
+            st->sum_w = a;
+            const bool bad = !(a > 0.0) || !(fabs(a) <= 1.79e308);  // TM:691
+            st->uniform_fallback = bad ? 1 : 0;
+            st->log_Sj = bad ? nan("") : (log(a) - log((double)N) + vmax);  // TM:697-698
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kRedThreads) weights_norm_kernel(double* __restrict__ w, long long N, const StageState* st,
+                                                                    double* out_logS) {
+    const double s = st->sum_w;
+    const bool uni = st->uniform_fallback != 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
+        w[i] = uni ? 1.0 / (double)N : w[i] / s;
+    if (out_logS && blockIdx.x == 0 && threadIdx.x == 0) *out_logS = st->log_Sj;
+}
+
+// K4a: cs = np.cumsum(w) with the exact left-to-right association, cs[N-1] := 1.0  (TM:195-197).
+// One warp: coalesced loads of 32 elements, the running sum travels lane to lane through shuffles.
+__global__ void __launch_bounds__(32) cumsum_serial_kernel(const double* __restrict__ w, long long N, double* __restrict__ cs) {
+    const int lane = threadIdx.x;
+    double carry = 0.0;
+    for (long long base = 0; base < N; base += 32) {
+        const long long i = base + lane;
+        const double x = (i < N) ? w[i] : 0.0;
+        double mine = 0.0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const double xj = __shfl_sync(0xffffffffu, x, j);
+            carry = carry + xj;  // same value in every lane; lane j keeps the prefix ending at element j
+            if (lane == j) mine = carry;
+        }
+        if (i < N) cs[i] = (i == N - 1) ? 1.0 : mine;
+    }
+}
+
+// K4b: idx_i = clip(searchsorted(cs, (u+i)/N, side='left'), 0, N-1)   (TM:194,198)
+__global__ void __launch_bounds__(kRedThreads) searchsorted_kernel(const double* __restrict__ cs, long long N, double u,
+                                                                    long long* __restrict__ idx) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const double pos = __ddiv_rn(__dadd_rn(u, (double)i), (double)N);
+        long long lo = 0, hi = N;
+        while (lo < hi) {
+            const long long mid = lo + ((hi - lo) >> 1);
+            if (cs[mid] < pos)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        idx[i] = (lo > N - 1) ? N - 1 : lo;
+    }
+}
+
+// K5a: moments = [sum w, sum w^2, sum w theta_j (j<d)]; one block-column per moment keeps it simple:
+// grid.y = 2 + d, grid.x blocks over particles.
+__global__ void __launch_bounds__(kRedThreads) wmoments_kernel(const double* __restrict__ theta, const double* __restrict__ w,
+                                                                long long N, int d, double* partial /*[gridDim.y][gridDim.x]*/,
+                                                                double* out /*[2+d]*/, unsigned int* tickets /*[gridDim.y]*/) {
+    __shared__ double sm[8];
+    const int m = blockIdx.y;
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const double wi = w[i];
+        s += (m == 0) ? wi : (m == 1) ? wi * wi : theta[i * d + (m - 2)] * wi;
+    }
+    s = block_reduce<false>(s, sm);
+    if (threadIdx.x == 0) partial[(size_t)m * gridDim.x + blockIdx.x] = s;
+    if (last_block(tickets + m)) {
+        double a = 0.0;
+        for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) a += __ldcg(partial + (size_t)m * gridDim.x + k);
+        a = block_reduce<false>(a, sm);
+        if (threadIdx.x == 0) out[m] = a;
+    }
+}
+
+__global__ void wmean_kernel(const double* moments, int d, double* mean) {
+    const int j = threadIdx.x;
+    if (j < d) mean[j] = moments[2 + j] / moments[0];  // np.average(..., weights=w)
+}
+
+// K5b: scatter[a,b] = sum_i (theta_ia - mean_a) ((theta_ib - mean_b) w_i); thread (a,b), particles staged in smem
+constexpr int kScatterChunk = 64;
+__global__ void __launch_bounds__(kRedThreads) wscatter_kernel(const double* __restrict__ theta, const double* __restrict__ w,
+                                                                long long N, int d, const double* __restrict__ mean,
+                                                                double* partial /*[gridDim.x][d*d]*/, double* out /*[d*d]*/,
+                                                                unsigned int* ticket) {
+    extern __shared__ double smem[];  // [kScatterChunk][d] centred thetas, then [kScatterChunk] weights
+    double* xs = smem;
+    double* ws = smem + (size_t)kScatterChunk * d;
+    const int dd = d * d;
+    // each thread owns up to ceil(dd / blockDim) output entries
+    const int per = (dd + blockDim.x - 1) / blockDim.x;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};  // d <= 32 -> dd <= 1024 -> per <= 4
+    for (long long base = (long long)blockIdx.x * kScatterChunk; base < N; base += (long long)gridDim.x * kScatterChunk) {
+        const int n = (int)((N - base < kScatterChunk) ? (N - base) : kScatterChunk);
+        __syncthreads();
+        for (int t = threadIdx.x; t < n * d; t += blockDim.x) xs[t] = theta[base * d + t] - mean[t % d];
+        for (int t = threadIdx.x; t < n; t += blockDim.x) ws[t] = w[base + t];
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = threadIdx.x + q * blockDim.x;
+            if (q < per && e < dd) {
+                const int a = e / d, b = e % d;
+                double s = acc[q];
+                for (int i = 0; i < n; ++i) s = fma(xs[i * d + a], xs[i * d + b] * ws[i], s);
+                acc[q] = s;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int e = threadIdx.x + q * blockDim.x;
+        if (q < per && e < dd) partial[(size_t)blockIdx.x * dd + e] = acc[q];
+    }
+    if (last_block(ticket)) {
+        for (int e = threadIdx.x; e < dd; e += blockDim.x) {
+            double s = 0.0;
+            for (int k = 0; k < (int)gridDim.x; ++k) s += __ldcg(partial + (size_t)k * dd + e);
+            out[e] = s;
+        }
+    }
+}
+
+// cov = scatter * (1/fact), fact = sum w - sum w^2 / sum w  (ddof = 1 with aweights)
+__global__ void wcov_final_kernel(const double* moments, const double* scatter, int d, double* cov, double* mean_out,
+                                  const double* mean) {
+    const double fact = moments[0] - moments[1] / moments[0];
+    const double rf = 1.0 / fact;
+    for (int e = threadIdx.x; e < d * d; e += blockDim.x) cov[e] = scatter[e] * rf;
+    if (mean_out)
+        for (int j = threadIdx.x; j < d; j += blockDim.x) mean_out[j] = mean[j];
+}
+
+}  // namespace hmx

@@ -1,0 +1,180 @@
+"""HamiltonEngine -- Python handle on one libhamilton context (one GPU).
+
+Arrays may be NumPy arrays (host pointers: the library stages them and synchronises) or CUDA torch
+tensors (device pointers: the call only enqueues work on the current torch stream).  There is no CPU
+fallback; construction raises when the library or a B200 is missing.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _abi
+
+
+class HmxError(RuntimeError):
+    pass
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _addr(x) -> Optional[int]:
+    if x is None:
+        return None
+    if _is_torch(x):
+        return x.data_ptr()
+    return x.ctypes.data
+
+
+class HamiltonEngine:
+    def __init__(self, config: _abi.HmxConfig, device: int = 0):
+        self._lib = _abi.load()
+        self._ctx = C.c_void_p()
+        self.config = config
+        self.device = int(device)
+        rc = self._lib.hmx_create(C.byref(self._ctx), C.byref(config), self.device)
+        if rc != 0:
+            msg = self._lib.hmx_last_error(None)
+            self._ctx = C.c_void_p()
+            raise HmxError(f"hmx_create failed ({rc}): {msg.decode() if msg else ''}")
+        self.n_cond = config.n_cond
+        self.n_steps = config.n_steps
+        self.n_obs_max = max(config.cond[k].n_obs for k in range(config.n_cond))
+
+    # -- plumbing ---------------------------------------------------------------------------------------
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self._lib.hmx_last_error(self._ctx)
+            raise HmxError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def close(self):
+        if self._ctx:
+            self._lib.hmx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def use_torch_stream(self):
+        """Enqueue on torch's current CUDA stream (needed before passing CUDA tensors)."""
+        import torch
+
+        self._check(self._lib.hmx_set_stream(self._ctx, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "hmx_set_stream")
+
+    def synchronize(self):
+        self._check(self._lib.hmx_synchronize(self._ctx), "hmx_synchronize")
+
+    # -- hot path ---------------------------------------------------------------------------------------
+    def loglik_batch(self, theta, cond_id=None, return_status=False, return_obs=False):
+        """logL[N] for FULL 20-vectors theta[N,20] (hmx_loglik_batch).  NumPy in -> NumPy out."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        if theta.ndim != 2 or theta.shape[1] != _abi.NTHETA:
+            raise ValueError("theta must have shape (N, 20)")
+        N = theta.shape[0]
+        cid = None if cond_id is None else np.ascontiguousarray(cond_id, dtype=np.int32)
+        if cid is not None and (cid.shape != (N,) or (N and (cid.min() < 0 or cid.max() >= self.n_cond))):
+            raise ValueError("cond_id must have shape (N,) with values in [0, n_cond)")
+        logL = np.empty(N, dtype=np.float64)
+        status = np.zeros(N, dtype=np.uint32) if return_status else None
+        iters = np.zeros(N, dtype=np.uint32) if return_status else None
+        obs = np.zeros((N, self.n_obs_max, _abi.NSTATE)) if return_obs else None
+        self._check(
+            self._lib.hmx_loglik_batch(self._ctx, _addr(theta), _addr(cid), N, _addr(logL), _addr(obs), _addr(status), _addr(iters)),
+            "hmx_loglik_batch",
+        )
+        out = [logL]
+        if return_status:
+            out += [status, iters]
+        if return_obs:
+            out += [obs]
+        return out[0] if len(out) == 1 else tuple(out)
+
+    def loglik_batch_device(self, theta, cond_id, logL, status=None, iters=None, obs_state=None):
+        """Device-resident variant: all arguments are CUDA torch tensors; only enqueues work."""
+        N = theta.shape[0]
+        self._check(
+            self._lib.hmx_loglik_batch(self._ctx, _addr(theta), _addr(cond_id), N, _addr(logL), _addr(obs_state), _addr(status), _addr(iters)),
+            "hmx_loglik_batch",
+        )
+
+    def trajectory_batch(self, theta, cond_id=None):
+        """g[N, n_steps+1, 12] (hmx_trajectory_batch)."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        N = theta.shape[0]
+        cid = None if cond_id is None else np.ascontiguousarray(cond_id, dtype=np.int32)
+        g = np.empty((N, self.n_steps + 1, _abi.NSTATE))
+        status = np.zeros(N, dtype=np.uint32)
+        iters = np.zeros(N, dtype=np.uint32)
+        self._check(self._lib.hmx_trajectory_batch(self._ctx, _addr(theta), _addr(cid), N, _addr(g), _addr(status), _addr(iters)), "hmx_trajectory_batch")
+        return g, status, iters
+
+    # -- stage arithmetic -------------------------------------------------------------------------------
+    def beta_step(self, logL, beta, target_ess_ratio=0.5, min_delta_beta=0.02, max_delta_beta=0.5):
+        logL = logL if _is_torch(logL) else np.ascontiguousarray(logL, dtype=np.float64)
+        db, ess = C.c_double(0.0), C.c_double(0.0)
+        self._check(
+            self._lib.hmx_beta_step(self._ctx, _addr(logL), logL.shape[0], beta, target_ess_ratio, min_delta_beta, max_delta_beta,
+                                    C.addressof(db), C.addressof(ess)),
+            "hmx_beta_step",
+        )
+        return db.value, ess.value
+
+    def weights(self, logL, delta_beta):
+        logL = np.ascontiguousarray(logL, dtype=np.float64)
+        w = np.empty_like(logL)
+        ls = C.c_double(0.0)
+        self._check(self._lib.hmx_weights(self._ctx, _addr(logL), logL.shape[0], delta_beta, _addr(w), C.addressof(ls)), "hmx_weights")
+        return w, ls.value
+
+    def resample(self, w, u):
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        idx = np.empty(w.shape[0], dtype=np.int64)
+        self._check(self._lib.hmx_resample(self._ctx, _addr(w), w.shape[0], float(u), _addr(idx)), "hmx_resample")
+        return idx
+
+    def weighted_cov(self, theta, w):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        N, d = theta.shape
+        mean, cov = np.empty(d), np.empty((d, d))
+        self._check(self._lib.hmx_weighted_cov(self._ctx, _addr(theta), _addr(w), N, d, _addr(mean), _addr(cov)), "hmx_weighted_cov")
+        return mean, cov
+
+    def weighted_moments(self, theta, w):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        N, d = theta.shape
+        m = np.empty(2 + d)
+        self._check(self._lib.hmx_weighted_moments(self._ctx, _addr(theta), _addr(w), N, d, _addr(m)), "hmx_weighted_moments")
+        return m
+
+    def weighted_scatter(self, theta, w, mean):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        N, d = theta.shape
+        s = np.empty((d, d))
+        self._check(self._lib.hmx_weighted_scatter(self._ctx, _addr(theta), _addr(w), N, d, _addr(mean), _addr(s)), "hmx_weighted_scatter")
+        return s
+
+    # -- measurement ------------------------------------------------------------------------------------
+    def set_timing(self, enabled: bool = True):
+        self._check(self._lib.hmx_set_timing(self._ctx, int(enabled)), "hmx_set_timing")
+
+    def counters(self) -> dict:
+        c = _abi.HmxCounters()
+        self._check(self._lib.hmx_get_counters(self._ctx, C.byref(c)), "hmx_get_counters")
+        return {f: getattr(c, f) for f, _ in _abi.HmxCounters._fields_}
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double(0.0)
+        self._check(self._lib.hmx_measure_fp64_peak(self._ctx, C.byref(v)), "hmx_measure_fp64_peak")
+        return v.value
