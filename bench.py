@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- particle-ODE likelihood evaluations per second on N B200s (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE.json configs[4], the synthetic likelihood throughput sweep -- per GPU
+4 conditions x 65,536 theta ~ U(prior bounds of the condition) (np.random.default_rng(20260101 + c + 97 rank)),
+production solver settings (dt=1e-4, 2500 steps, c=25, alpha=0, Kp1=1e-4, K_hill=0.05, n_hill=4), TSM
+variance on.  One evaluation = one (theta, condition) pair = one 2500-step implicit solve + its Gaussian
+log-likelihood.  Weak scaling: the per-GPU batch is fixed, ranks hold disjoint particles.
+
+A "step" is one pass of the hot path over one batch:
+    ODE + likelihood kernels on this rank's particles -> all-gather of the log-likelihoods (N > 1) ->
+    per-condition stage arithmetic on the gathered population (delta-beta bisection, weights + evidence,
+    systematic resampling, weighted covariance from shard-local partial sums + all-reduce).
+`value`  : inputs resident in HBM, timed with CUDA events on the launching stream, barrier + synchronize on
+           both sides, max over ranks.
+`e2e`    : the same step through the public host-facing API (NumPy buffers: theta/cond_id H2D and
+           logL/weights/indices/covariance D2H inside the timed region).
+`roofline`: FP64 FMA pipe (the path is compute bound; HBM traffic is ~1.2 KB per 2e7-flop evaluation).
+`cpu_baseline` / `--impl reference`: the oracle's C restatement of the reference algorithm (kind "port": the
+           reference itself is Python+numba and its tree does not travel to the GPU box) on all host threads.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_PER_COND = 65536
+N_COND = 4
+METRIC = "particle_ode_likelihood_evals_per_sec"
+UNIT = "evals/s"
+
+# Executed FP64 flops (DFMA = 2, DMUL = DADD = 1) of the ODE kernel per residual evaluation ("trip") and per
+# quasi-Newton direction solve, calibrated from the ncu capture profiles/r01a_ode_kernel_first.json
+# (thread-level sass op counters / the kernel's own trip and iteration counters; split by the static SASS
+# ratio of residual() : direction()).  DESIGN.md section "Roofline accounting" has the derivation.
+FLOPS_PER_RESIDUAL = 376.0
+FLOPS_PER_DIRECTION = 1093.0
+# the reference-equivalent count of SURVEY.md section 8(d): dense Q + K + dgesv per iteration, Q per extra trial
+REF_FLOPS_PER_ITER = 2778.0
+REF_FLOPS_PER_TRIAL = 384.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                power.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synth_batch(rank: int):
+    from tmcmc202601_b200 import workloads
+
+    wl = workloads.four_condition_workload(N_PER_COND, seed=20260101 + 97 * rank)
+    return wl
+
+
+def cpu_baseline(wl, budget_s: float = 12.0, max_evals: int = 8192) -> dict:
+    """The oracle port on all host threads, on a bounded prefix-sample of the same workload (equal share per condition)."""
+    from oracle import oracle as orc
+
+    cores = os.cpu_count() or 1
+    per = max(cores, 8)
+    idx_by_cond = [np.nonzero(wl.cond_id == c)[0] for c in range(N_COND)]
+    done, t_total, pos = 0, 0.0, 0
+    while t_total < budget_s and done < max_evals:
+        sel = np.concatenate([ix[pos:pos + per] for ix in idx_by_cond])
+        if sel.size == 0:
+            break
+        t0 = time.perf_counter()
+        orc.evaluate_hmx(wl.config, wl.theta[sel], wl.cond_id[sel], n_threads=cores)
+        t_total += time.perf_counter() - t0
+        done += sel.size
+        pos += per
+    return {"value": done / t_total if t_total > 0 else 0.0, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {done} evaluations of the workload ({done // N_COND} per condition), oracle/hamilton_oracle.c on {cores} pthreads, {t_total:.1f} s"}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Python+numba original does not travel) on the host."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = synth_batch(0)
+    from oracle import oracle as orc
+
+    cores = os.cpu_count() or 1
+    per_step = max(cores * 64, 256)  # evaluations per step: a bounded sample, ~2-3 s of CPU work per step
+    sel_all = np.concatenate([np.nonzero(wl.cond_id == c)[0][: (args.steps + args.warmup) * per_step // N_COND + per_step] for c in range(N_COND)])
+    rng = np.random.default_rng(0)
+    rng.shuffle(sel_all)
+    times = []
+    for s in range(args.warmup + args.steps):
+        sel = sel_all[s * per_step:(s + 1) * per_step]
+        t0 = time.perf_counter()
+        orc.evaluate_hmx(wl.config, wl.theta[sel], wl.cond_id[sel], n_threads=cores)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = per_step * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus, per_step_note=f"each step = a bounded sample of {per_step} evaluations of the same workload"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{per_step} evaluations per step x {len(times)} steps, oracle/hamilton_oracle.c on {cores} pthreads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus: int, per_step_note: str = "") -> dict:
+    return {
+        "workload": "BASELINE.json configs[4]: synthetic likelihood throughput, 4 conditions (Commensal/Dysbiotic x Static/HOBIC) x "
+                    f"{N_PER_COND} theta ~ U(prior bounds) per GPU, Hamilton 5-species ODE dt=1e-4 x 2500 steps, K_hill=0.05 n_hill=4, TSM variance on",
+        "evals_per_gpu_per_step": N_PER_COND * N_COND, "global_evals_per_step": N_PER_COND * N_COND * n_gpus,
+        "n_steps_ode": 2500, "parallelism": f"particles sharded over {n_gpus} GPU(s), logL all-gather + covariance all-reduce per step",
+        "l2_policy": "inputs+scratch per step (42 MB theta + 252 MB observation pairs per GPU) exceed the 126 MB L2; no flush needed",
+        "note": per_step_note,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from tmcmc202601_b200.engine import HamiltonEngine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    wl = synth_batch(rank)
+    M = wl.theta.shape[0]
+    eng = HamiltonEngine(wl.config, device=local_rank)
+    eng.use_torch_stream()
+    fp64_peak = eng.measure_fp64_peak()
+
+    # ---- device-resident buffers ------------------------------------------------------------------------
+    th_d = torch.from_numpy(wl.theta).to(dev)
+    cid_d = torch.from_numpy(wl.cond_id).to(dev)
+    ll_d = torch.empty(M, dtype=torch.float64, device=dev)
+    ll_all = torch.empty(world * M, dtype=torch.float64, device=dev) if world > 1 else ll_d
+    w_d = torch.empty(world * N_PER_COND, dtype=torch.float64, device=dev)
+    idx_d = torch.empty(world * N_PER_COND, dtype=torch.int64, device=dev)
+    mom_d = torch.empty(22, dtype=torch.float64, device=dev)
+    mean_d = torch.empty(20, dtype=torch.float64, device=dev)
+    sc_d = torch.empty(400, dtype=torch.float64, device=dev)
+    # the batch is sorted by condition: condition c of rank r sits at [c*N_PER_COND, (c+1)*N_PER_COND) of its block
+    gather_idx = torch.cat([torch.arange(c * N_PER_COND, (c + 1) * N_PER_COND, device=dev) + r * M for c in range(N_COND) for r in range(world)]
+                           ).reshape(N_COND, world * N_PER_COND)
+    u_draw = np.random.default_rng(1234).random(1024)  # identical on every replica
+
+    def stage_arithmetic(step: int):
+        """Per-condition stage arithmetic on the gathered population; covariance from shard-local partial sums."""
+        for c in range(N_COND):
+            pop = ll_all[gather_idx[c]] if world > 1 else ll_d[c * N_PER_COND:(c + 1) * N_PER_COND]
+            db, _ = eng.beta_step(pop, 0.0, 0.5, 0.02, 0.5)
+            eng.weights_device(pop, db, w_d)
+            eng.resample_device(w_d, float(u_draw[(step * N_COND + c) % 1024]), idx_d)
+            lo = c * N_PER_COND
+            w_loc = w_d[rank * N_PER_COND:(rank + 1) * N_PER_COND]
+            eng.weighted_moments_device(th_d[lo:lo + N_PER_COND], w_loc, mom_d)
+            if world > 1:
+                dist.all_reduce(mom_d)
+            torch.div(mom_d[2:], mom_d[0], out=mean_d)
+            eng.weighted_scatter_device(th_d[lo:lo + N_PER_COND], w_loc, mean_d, sc_d)
+            if world > 1:
+                dist.all_reduce(sc_d)
+
+    def device_step(step: int):
+        eng.loglik_batch_device(th_d, cid_d, ll_d)
+        if world > 1:
+            dist.all_gather_into_tensor(ll_all, ll_d)
+        stage_arithmetic(step)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for s in range(args.warmup):
+        device_step(s)
+    barrier()
+    launches0 = eng.counters()["kernel_launches"]
+    eng.set_timing(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ode_ms, iters_sum, trips_sum = [], 0, 0
+    barrier()
+    ev0.record()
+    for s in range(args.steps):
+        device_step(args.warmup + s)
+        c = eng.counters()  # synchronises this rank's stream: the step's host scalars are needed anyway
+        ode_ms.append(c["last_ode_kernel_ms"])
+        iters_sum += c["newton_iters"]
+        trips_sum += c["q_evals"]
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = eng.counters()["kernel_launches"] - launches0
+    eng.set_timing(False)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = world * M * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the host-facing API ---------------------------------------------------------
+    th_h = torch.from_numpy(wl.theta).pin_memory().numpy()
+    cid_h = torch.from_numpy(wl.cond_id).pin_memory().numpy()
+
+    def host_step(step: int):
+        logL = eng.loglik_batch(th_h, cid_h)  # H2D theta + cond_id, D2H logL
+        if world > 1:
+            g = torch.from_numpy(logL).to(dev)
+            dist.all_gather_into_tensor(ll_all, g)
+            full = ll_all.cpu().numpy().reshape(world, N_COND, N_PER_COND)
+        else:
+            full = logL.reshape(1, N_COND, N_PER_COND)
+        out = None
+        for c in range(N_COND):
+            pop = np.ascontiguousarray(full[:, c, :].reshape(-1))
+            db, _ = eng.beta_step(pop, 0.0, 0.5, 0.02, 0.5)
+            w, _ = eng.weights(pop, db)
+            idx = eng.resample(w, float(u_draw[(step * N_COND + c) % 1024]))
+            lo = c * N_PER_COND
+            w_loc = w[rank * N_PER_COND:(rank + 1) * N_PER_COND]
+            mom = eng.weighted_moments(th_h[lo:lo + N_PER_COND], w_loc)
+            if world > 1:
+                mt = torch.from_numpy(mom).to(dev)
+                dist.all_reduce(mt)
+                mom = mt.cpu().numpy()
+            sc = eng.weighted_scatter(th_h[lo:lo + N_PER_COND], w_loc, mom[2:] / mom[0])
+            if world > 1:
+                st = torch.from_numpy(sc).to(dev)
+                dist.all_reduce(st)
+                sc = st.cpu().numpy()
+            out = (idx, sc)
+        return out
+
+    host_step(0)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_steps = max(2, min(args.steps, 4))
+    for s in range(e2e_steps):
+        host_step(1 + s)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)  # e1 is recorded after the last host-facing call returned (each call synchronises)
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * M * e2e_steps / (float(te.item()) * 1e-3)
+    pop_n = world * N_PER_COND
+    # bytes the host-facing calls copy per step: theta + cond_id in, logL out; per condition the population logL
+    # (beta_step, weights), w (resample), theta_c + w_c twice (moments, scatter) and the mean in; w, idx, 3 scalars,
+    # 22 moments and the 20x20 scatter out
+    h2d = M * (20 * 8 + 4) + N_COND * (3 * pop_n * 8 + 2 * N_PER_COND * (20 * 8 + 8) + 20 * 8)
+    d2h = M * 8 + N_COND * (2 * pop_n * 8 + 3 * 8 + 22 * 8 + 400 * 8)
+
+    # ---- roofline of the dominant kernel (ode_kernel): executed FP64 flops / CUDA-event duration ---------
+    ode_avg_ms = float(np.mean(ode_ms))
+    flops_per_launch = (FLOPS_PER_RESIDUAL * trips_sum + FLOPS_PER_DIRECTION * iters_sum) / args.steps
+    achieved = flops_per_launch / (ode_avg_ms * 1e-3) / 1e12
+    ref_equiv = ((REF_FLOPS_PER_ITER * iters_sum + REF_FLOPS_PER_TRIAL * max(trips_sum - iters_sum - 2500 * M * args.steps, 0)) / args.steps
+                 / (ode_avg_ms * 1e-3) / 1e12)
+    roofline = {
+        "bound": "fp64", "kernel": "hmx::ode_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+        "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+        "peak_source": "measured live by hmx_measure_fp64_peak (register-resident DFMA loop); MEASURED_PEAKS.json has no FP64 entry "
+                       "(nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2)",
+        "kernel_ms_per_launch": ode_avg_ms, "kernel_share_of_step": ode_avg_ms * args.steps / elapsed_ms,
+        "flops_per_launch": flops_per_launch, "newton_iters_per_eval": iters_sum / (M * args.steps),
+        "residual_evals_per_eval": trips_sum / (M * args.steps),
+        "reference_equivalent_tflops": ref_equiv,
+        "hbm_algorithmic_bytes_per_eval": 20 * 8 + 4 + 5 * 24 * 8 + 12 + 8,
+    }
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(wl)
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -140,6 +140,12 @@ int hmx_weighted_moments(hmx_ctx* ctx, const double* theta, const double* w, int
 int hmx_weighted_scatter(hmx_ctx* ctx, const double* theta, const double* w, int64_t N, int32_t d,
                          const double* mean, double* scatter);
 
+/* replaces: log_likelihood_sparse(mu, sig, data, sigma_obs, rho=0, weights) (EV:237-371), diagonal branch.
+ * mu, sig, data, sigma_obs, weights: [n_obs,5] row-major (sigma_obs pre-broadcast; weights may be NULL = 1).
+ * *logL receives the scalar; n_obs may exceed HMX_MAX_OBS here. */
+int hmx_log_likelihood_sparse(hmx_ctx* ctx, const double* mu, const double* sig, const double* data,
+                              const double* sigma_obs, const double* weights, int32_t n_obs, double* logL);
+
 /* ---- measurement support ------------------------------------------------------------------------- */
 typedef struct {
     int64_t evals;         /* evaluations processed by the last hmx_loglik_batch / hmx_trajectory_batch */

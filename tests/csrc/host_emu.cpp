@@ -88,6 +88,32 @@ int emu_evaluate(const hmx_config* cfg, int cond, const double* theta, double* g
     return 0;
 }
 
+// struct layout checks for the ctypes mirror (tmcmc202601_b200/_abi.py)
+int emu_sizeof_config(void) { return (int)sizeof(hmx_config); }
+int emu_sizeof_cond(void) { return (int)sizeof(hmx_cond); }
+int emu_sizeof_counters(void) { return (int)sizeof(hmx_counters); }
+int emu_validate(const hmx_config* cfg) {
+    const char* why;
+    return validate_config(cfg, &why);
+}
+
+// the two 5x5 solvers of hmx_model.cuh on a caller-supplied system M[5][7]; returns the smallest pivot
+double emu_solve5x2(const double* M, double* X, int pivoted) {
+    if (pivoted) {
+        solve5x2_pivoted(M, X);
+        return 0.0;
+    }
+    double S[5][7];
+    for (int r = 0; r < 5; ++r)
+        for (int c = 0; c < 7; ++c) S[r][c] = M[r * 7 + c];
+    const double pmin = solve5x2_natural(S);
+    for (int r = 0; r < 5; ++r) {
+        X[r] = S[r][5];
+        X[5 + r] = S[r][6];
+    }
+    return pmin;
+}
+
 // residual and structured quasi-Newton direction at one point
 int emu_direction(const hmx_config* cfg, const double* theta, const double* g_new, const double* g_old,
                   double* Q, double* delta) {

@@ -188,7 +188,7 @@ def main():
     # ------------------------------------------------------------------ stage arithmetic KATs
     tm = m["tmcmc"]
     rs_w, rs_u, rs_idx = [], [], []
-    for seed, N in ((1, 7), (2, 64), (3, 1000), (4, 1000), (5, 4096), (6, 100000)):
+    for seed, N in ((1, 7), (2, 64), (3, 1000), (4, 1000), (5, 4096), (6, 30000)):
         r = np.random.default_rng(seed)
         ll = r.normal(size=N) * (3.0 if seed % 2 else 30.0)
         w = np.exp(ll - ll.max())
@@ -214,7 +214,8 @@ def main():
     ss = res.stage_summary
     np.savez_compressed(
         OUT / "stage_kat.npz",
-        resample_w=np.array(rs_w, dtype=object), resample_u=np.array(rs_u), resample_idx=np.array(rs_idx, dtype=object),
+        resample_n=len(rs_w), resample_u=np.array(rs_u),
+        **{f"resample_w{k}": a for k, a in enumerate(rs_w)}, **{f"resample_idx{k}": a for k, a in enumerate(rs_idx)},
         toy_bounds=np.array(toy_bounds), toy_seed=1234, toy_n_particles=300, toy_n_stages=30, toy_n_mutation_steps=3,
         toy_beta_schedule=np.array(res.beta_schedule), toy_samples=res.samples, toy_logL=res.logL_values,
         toy_theta_MAP=res.theta_MAP, toy_log_evidence=res.log_evidence,

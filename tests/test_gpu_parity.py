@@ -1,0 +1,188 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libhamilton.so), against the CPU oracle on
+the same seeded inputs, against the committed golden vectors of the LIVE reference, and -- at sizes the
+oracle cannot cover -- through size-independent properties.
+
+Bar (BASELINE.json north_star): trajectories and log-likelihoods within 1e-9 relative in FP64."""
+import json
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN
+from oracle import oracle as orc
+from tmcmc202601_b200 import _abi, workloads
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def engines(built):
+    from tmcmc202601_b200.engine import HamiltonEngine
+
+    made = []
+
+    def make(cfg):
+        e = HamiltonEngine(cfg, device=0)
+        made.append(e)
+        return e
+
+    yield make
+    for e in made:
+        e.close()
+
+
+def _rel(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def test_four_condition_batch_matches_oracle(engines):
+    wl = workloads.four_condition_workload(48, seed=20260101, interleave=True)
+    eng = engines(wl.config)
+    logL, st, it = eng.loglik_batch(wl.theta, wl.cond_id, return_status=True)
+    ref, rst, rit, _ = orc.evaluate_hmx(wl.config, wl.theta, wl.cond_id, details=True)
+    rel = _rel(logL, ref)
+    print(f"logL rel error: max {rel.max():.2e}, p99 {np.quantile(rel, 0.99):.2e}, median {np.median(rel):.2e}")
+    assert rel.max() < REL
+    assert np.array_equal(it.astype(np.int64), rit)  # same quasi-Newton iterate sequence, evaluation by evaluation
+    assert np.array_equal(st & 1, rst & 1)
+    c = eng.counters()
+    assert c["evals"] == logL.size and c["newton_iters"] == int(rit.sum()) and c["q_evals"] >= c["newton_iters"]
+
+
+def test_golden_evaluator_values_of_live_reference(engines):
+    k = np.load(GOLDEN / "evaluator_kat.npz")
+    conds = workloads.load_conditions()
+    kw = json.loads(str(k["solver_kwargs"]))
+    for key in sorted(set(map(str, k["cond"]))):
+        cd = conds[key]
+        sig = cd["sigma_scalar"] if key.endswith("legacy_1k30") else cd["sigma_obs"]
+        structs = [workloads.cond_struct(cd, sigma_obs=sig), workloads.cond_struct(cd, sigma_obs=sig, tsm_variance=False)]
+        eng = engines(_abi.make_config(structs, **kw))
+        sel = [i for i, c in enumerate(k["cond"]) if str(c) == key]
+        th = k["theta_full"][sel]
+        ll = eng.loglik_batch(th, np.zeros(len(sel), np.int32))
+        ll0 = eng.loglik_batch(th, np.ones(len(sel), np.int32))
+        assert _rel(ll, k["logL"][sel]).max() < REL, key
+        assert _rel(ll0, k["logL_det"][sel]).max() < REL, key
+
+
+def test_golden_trajectories_of_live_reference(engines):
+    k = np.load(GOLDEN / "solver_kat.npz")
+    from tmcmc202601_b200.solver import BiofilmNewtonSolver5S
+
+    worst = 0.0
+    for i, name in enumerate(k["names"]):
+        kw = json.loads(str(k["kwargs"][i]))
+        rows = k["rows"][i]
+        rows = rows[rows >= 0]
+        s = BiofilmNewtonSolver5S(**kw)
+        t_arr, g = s.run_deterministic(k["theta"][i])
+        assert g.shape == (kw["maxtimestep"] + 1, 12) and t_arr.shape == (kw["maxtimestep"] + 1,)
+        assert t_arr[0] == 0.0 and t_arr[-1] == pytest.approx(kw["maxtimestep"] * kw["dt"])
+        rel = _rel(g[rows], k["g_rows"][i][: len(rows)])
+        worst = max(worst, rel.max())
+        assert rel.max() < REL, (str(name), rel.max())
+        s._engine.close()
+    print(f"trajectory rows vs live numba reference: worst rel {worst:.2e}")
+
+
+@pytest.mark.parametrize("extra", [
+    dict(workloads.T500_SOLVER), dict(workloads.T500_SOLVER, K_hill=0.05, n_hill=2.0),
+    dict(workloads.PRODUCTION_SOLVER, n_hill=1.0), dict(workloads.PRODUCTION_SOLVER, n_hill=2.5),
+    dict(workloads.PRODUCTION_SOLVER, n_hill=3.0, alpha_const=2.0),
+    dict(workloads.PRODUCTION_SOLVER, eta_vec=[1.0, 1.3, 0.8, 1.1, 0.9], eta_phi_vec=[1.2, 0.7, 1.0, 1.5, 0.95]),
+    dict(workloads.PRODUCTION_SOLVER, maxtimestep=300, max_newton_iter=7),
+], ids=["t500", "t500_hill", "n1", "n2.5", "n3_alpha", "eta", "maxiter7"])
+def test_solver_variants_match_oracle(engines, extra):
+    cd = workloads.load_conditions()["Dysbiotic_HOBIC"]
+    T = extra["maxtimestep"]
+    idx = np.unique(np.clip((cd["idx_sparse"] * T) // 2500, 1, T))
+    hc = _abi.make_cond(cd["data"][: len(idx)], idx, cd["sigma_obs"][: len(idx)], 0.2 if T == 500 else cd["phi_init"],
+                        active_theta_indices=cd["active_indices"])
+    cfg = _abi.make_config([hc], **extra)
+    eng = engines(cfg)
+    th = workloads.sample_prior(cd["bounds"], 24, np.random.default_rng(3))
+    logL, st, it = eng.loglik_batch(th, None, return_status=True)
+    ref, rst, rit, _ = orc.evaluate_hmx(cfg, th, None, details=True)
+    assert _rel(logL, ref).max() < REL
+    assert np.array_equal(it.astype(np.int64), rit)
+    g, _, _ = eng.trajectory_batch(th[:3])
+    (ocfg, _), = orc.from_hmx_config(cfg)
+    for j in range(3):
+        _, go, *_ = orc.run_deterministic(ocfg, th[j])
+        assert _rel(g[j], go).max() < REL
+
+
+def test_obs_state_output_equals_trajectory_rows(engines):
+    wl = workloads.single_condition_workload("Commensal_HOBIC", 6, seed=5)
+    eng = engines(wl.config)
+    logL, obs = eng.loglik_batch(wl.theta, wl.cond_id, return_obs=True)
+    g, _, _ = eng.trajectory_batch(wl.theta, wl.cond_id)
+    idx = np.array(wl.config.cond[0].idx_sparse[:5])
+    assert np.array_equal(obs, g[:, idx, :])  # same kernel arithmetic -> bitwise
+
+
+def test_use_absolute_volume_and_weights(engines):
+    cd = workloads.load_conditions()["Dysbiotic_Static"]
+    from tmcmc202601_b200.evaluator import build_likelihood_weights
+
+    W = build_likelihood_weights(5, 5)
+    structs = [workloads.cond_struct(cd, weights=W), workloads.cond_struct(cd, use_absolute_volume=True)]
+    cfg = _abi.make_config(structs, **workloads.PRODUCTION_SOLVER)
+    eng = engines(cfg)
+    th = workloads.sample_prior(cd["bounds"], 10, np.random.default_rng(8))
+    th = np.vstack([th, th])
+    cid = np.repeat([0, 1], 10).astype(np.int32)
+    ref = orc.evaluate_hmx(cfg, th, cid)
+    assert _rel(eng.loglik_batch(th, cid), ref).max() < REL
+
+
+def test_edge_cases_empty_single_nonfinite(engines):
+    wl = workloads.single_condition_workload("Dysbiotic_HOBIC", 4, seed=1)
+    eng = engines(wl.config)
+    assert eng.loglik_batch(np.zeros((0, 20))).shape == (0,)
+    one = eng.loglik_batch(wl.theta[:1])
+    assert one.shape == (1,) and one[0] == eng.loglik_batch(wl.theta)[0]
+    bad = wl.theta.copy()
+    bad[1, 0] = np.nan
+    bad[2, 14] = np.inf
+    ll, st, _ = eng.loglik_batch(bad, return_status=True)
+    assert ll[1] == -1e20 and ll[2] == -1e20 and (st[1] & 1) and (st[2] & 1)  # the reference's sentinel, never an error
+    assert ll[0] == one[0] and not (st[0] & 1) and np.isfinite(ll[3])
+    with pytest.raises(ValueError):
+        eng.loglik_batch(wl.theta, np.full(4, 7, np.int32))
+    with pytest.raises(ValueError):
+        eng.loglik_batch(np.zeros((3, 19)))
+
+
+def test_device_pointer_path_is_bitwise_equal_to_host_path(engines):
+    import torch
+
+    wl = workloads.four_condition_workload(40, seed=77)
+    eng = engines(wl.config)
+    host = eng.loglik_batch(wl.theta, wl.cond_id)
+    dev = torch.device("cuda", 0)
+    th = torch.from_numpy(wl.theta).to(dev)
+    cid = torch.from_numpy(wl.cond_id).to(dev)
+    out = torch.empty(th.shape[0], dtype=torch.float64, device=dev)
+    eng.use_torch_stream()
+    eng.loglik_batch_device(th, cid, out)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), host)
+    # and deterministic launch to launch
+    assert np.array_equal(eng.loglik_batch(wl.theta, wl.cond_id), host)
+
+
+def test_large_batch_is_order_independent(engines):
+    """Beyond oracle sizes: 60k evaluations (more than one resident wave, dynamic work fetch) must give every
+    duplicate of an input the bit-identical result wherever it lands in the batch."""
+    wl = workloads.four_condition_workload(64, seed=9)
+    eng = engines(wl.config)
+    base = eng.loglik_batch(wl.theta, wl.cond_id)
+    rng = np.random.default_rng(0)
+    pick = rng.integers(0, wl.theta.shape[0], size=60000)
+    big = eng.loglik_batch(wl.theta[pick], wl.cond_id[pick])
+    assert np.array_equal(big, base[pick])
+    assert np.isfinite(big).all() and (big > -1e19).all()

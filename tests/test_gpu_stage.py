@@ -1,0 +1,115 @@
+"""Per-stage TMCMC kernels through the C ABI against the oracle / NumPy / the live reference's golden
+resampling indices.  Bars: resampling indices bit-exact; delta-beta, weights, evidence, covariance <= 1e-12."""
+import numpy as np
+import pytest
+
+from helpers import GOLDEN
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng(built):
+    from tmcmc202601_b200.tmcmc import GpuStageOps
+
+    return GpuStageOps().engine
+
+
+def test_resample_bit_exact_with_live_reference_golden(eng):
+    k = np.load(GOLDEN / "stage_kat.npz")
+    for c in range(int(k["resample_n"])):
+        idx = eng.resample(k[f"resample_w{c}"], float(k["resample_u"][c]))
+        assert idx.dtype == np.int64 and np.array_equal(idx, k[f"resample_idx{c}"])
+
+
+@pytest.mark.parametrize("N", [1, 2, 31, 32, 33, 1000, 4097, 250000])
+def test_resample_bit_exact_with_numpy(eng, N):
+    rng = np.random.default_rng(N)
+    w = rng.random(N) ** 6
+    w /= w.sum()
+    for u in (0.0, rng.random(), 1.0 - 2.0**-53):
+        cs = np.cumsum(w)
+        cs[-1] = 1.0
+        ref = np.clip(np.searchsorted(cs, (u + np.arange(N)) / N), 0, N - 1)
+        got = eng.resample(w, u)
+        assert np.array_equal(got, ref)
+        assert np.all(np.diff(got) >= 0)  # sortedness: a size-independent property of systematic resampling
+
+
+def test_resample_degenerate_and_counts(eng):
+    w = np.zeros(1000)
+    w[123] = 1.0
+    assert np.all(eng.resample(w, 0.7) == 123)
+    N = 2_000_000  # beyond oracle sizes: offspring counts are floor/ceil of N w_i
+    rng = np.random.default_rng(5)
+    w = rng.random(N)
+    w /= w.sum()
+    idx = eng.resample(w, 0.25)
+    counts = np.bincount(idx, minlength=N)
+    assert counts.sum() == N and np.all(np.abs(counts - N * w) < 1.0 + 1e-6) and np.all(np.diff(idx) >= 0)
+
+
+@pytest.mark.parametrize("N,scale", [(7, 1.0), (1000, 5.0), (1000, 80.0), (100000, 20.0)])
+def test_beta_step_and_weights(eng, N, scale):
+    rng = np.random.default_rng(N + int(scale))
+    logL = rng.normal(size=N) * scale
+    logL[rng.integers(0, N)] = -1e20  # a failed solve in the population
+    for beta in (0.0, 0.4, 0.99):
+        db, ess = eng.beta_step(logL, beta, 0.5, 0.02, 0.5)
+        db_o, ess_o = orc.beta_step(logL, beta, 0.5, 0.02, 0.5)
+        assert abs(db - db_o) <= 1e-12 * db_o
+        assert (np.isnan(ess) and np.isnan(ess_o)) or abs(ess - ess_o) <= 1e-10 * ess_o
+        w, ls = eng.weights(logL, db)
+        w_o, ls_o, _ = orc.weights(logL, db)
+        assert np.allclose(w, w_o, rtol=1e-12, atol=1e-300) and abs(w.sum() - 1.0) < 1e-12
+        assert abs(ls - ls_o) <= 1e-12 * max(1.0, abs(ls_o))
+
+
+def test_weights_uniform_fallback(eng):
+    w, ls = eng.weights(np.full(16, -np.inf), 0.3)
+    assert np.allclose(w, 1.0 / 16) and np.isnan(ls)
+
+
+@pytest.mark.parametrize("N,d", [(10, 1), (1000, 20), (1001, 9), (50000, 20), (300, 32)])
+def test_weighted_cov_matches_numpy(eng, N, d):
+    rng = np.random.default_rng(N * d)
+    theta = rng.normal(size=(N, d)) * (1.0 + rng.random(d)) + rng.normal(size=d)
+    w = rng.random(N) ** 3
+    w /= w.sum()
+    mean, cov = eng.weighted_cov(theta, w)
+    ref = np.atleast_2d(np.cov(theta.T, aweights=w))
+    assert np.allclose(cov, ref, rtol=1e-11, atol=1e-14 * np.abs(ref).max())
+    assert np.allclose(cov, cov.T, rtol=0, atol=1e-18) and np.allclose(mean, np.average(theta, axis=0, weights=w), rtol=1e-13)
+    # the two shard-local halves (multi-GPU path) reproduce it
+    half = N // 2
+    mom = eng.weighted_moments(theta[:half], w[:half]) + eng.weighted_moments(theta[half:], w[half:]) if half else eng.weighted_moments(theta, w)
+    m = mom[2:] / mom[0]
+    sc = eng.weighted_scatter(theta[:half], w[:half], m) + eng.weighted_scatter(theta[half:], w[half:], m) if half else eng.weighted_scatter(theta, w, m)
+    assert np.allclose(sc / (mom[0] - mom[1] / mom[0]), ref, rtol=1e-11, atol=1e-14 * np.abs(ref).max())
+
+
+def test_log_likelihood_sparse(eng):
+    from tmcmc202601_b200.evaluator import build_likelihood_weights, log_likelihood_sparse
+
+    rng = np.random.default_rng(2)
+    mu, data = rng.random((6, 5)), rng.random((6, 5))
+    sig = rng.random((6, 5)) * 1e-3
+    for sigma in (0.23, np.array([0.1, 0.2, 0.3, 0.1, 0.05]), rng.random((6, 5)) + 0.01):
+        for W in (None, build_likelihood_weights(6, 5)):
+            got = log_likelihood_sparse(mu, sig, data, sigma, rho=0.0, weights=W)
+            ref = orc.log_likelihood_sparse(mu, sig, data, sigma, W)
+            assert abs(got - ref) <= 1e-12 * abs(ref)
+    h = {}
+    v = log_likelihood_sparse(mu, np.full((6, 5), -1.0), data, 0.0, health=h)  # negative variance -> 1e-20 floor
+    assert np.isfinite(v) and h["n_var_total_clipped"] == 30 and h["n_var_raw_negative"] == 30
+
+
+def test_systematic_resample_api(eng):
+    from tmcmc202601_b200.tmcmc import systematic_resample
+
+    w = np.random.default_rng(1).random(500)
+    w /= w.sum()
+    idx = systematic_resample(w, np.random.default_rng(42))
+    u = np.random.default_rng(42).random()
+    assert np.array_equal(idx, orc.resample(w, u))

@@ -73,7 +73,8 @@ class HmxCounters(C.Structure):
 EXPORTS = [
     "hmx_create", "hmx_destroy", "hmx_last_error", "hmx_set_stream", "hmx_synchronize", "hmx_abi_version",
     "hmx_loglik_batch", "hmx_trajectory_batch", "hmx_beta_step", "hmx_weights", "hmx_resample",
-    "hmx_weighted_cov", "hmx_weighted_moments", "hmx_weighted_scatter", "hmx_get_counters", "hmx_set_timing",
+    "hmx_weighted_cov", "hmx_weighted_moments", "hmx_weighted_scatter", "hmx_log_likelihood_sparse", "hmx_get_counters",
+    "hmx_set_timing",
     "hmx_measure_fp64_peak",
 ]
 
@@ -209,6 +210,7 @@ def load() -> C.CDLL:
     lib.hmx_weighted_cov.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp, vp]
     lib.hmx_weighted_moments.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp]
     lib.hmx_weighted_scatter.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp, vp]
+    lib.hmx_log_likelihood_sparse.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int32, vp]
     lib.hmx_get_counters.argtypes = [vp, C.POINTER(HmxCounters)]
     lib.hmx_set_timing.argtypes = [vp, C.c_int32]
     lib.hmx_measure_fp64_peak.argtypes = [vp, dp]

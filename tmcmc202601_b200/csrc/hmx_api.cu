@@ -597,6 +597,40 @@ int hmx_weighted_cov(hmx_ctx* ctx, const double* theta, const double* w, int64_t
     return HMX_OK;
 }
 
+int hmx_log_likelihood_sparse(hmx_ctx* ctx, const double* mu, const double* sig, const double* data,
+                              const double* sigma_obs, const double* weights, int32_t n_obs, double* logL) {
+    if (!ctx) return HMX_ERR_INVALID;
+    if (n_obs < 0 || !mu || !sig || !data || !sigma_obs || !logL) return fail(ctx, HMX_ERR_INVALID, "hmx_log_likelihood_sparse: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    const size_t bytes = (size_t)n_obs * 5 * sizeof(double);
+    // five small inputs share one staging buffer
+    if ((rc = ensure(ctx, ctx->st_in2, 5 * bytes + 64))) return rc;
+    const double* src[5] = {mu, sig, data, sigma_obs, weights};
+    const double* dev[5];
+    for (int k = 0; k < 5; ++k) {
+        if (!src[k]) {
+            dev[k] = nullptr;
+        } else if (is_device_ptr(src[k])) {
+            dev[k] = src[k];
+        } else {
+            double* dst = (double*)((char*)ctx->st_in2.p + k * bytes);
+            if (bytes) CU(cudaMemcpyAsync(dst, src[k], bytes, cudaMemcpyHostToDevice, ctx->stream));
+            dev[k] = dst;
+        }
+    }
+    const bool out_dev = is_device_ptr(logL);
+    double* d_out = out_dev ? logL : ctx->d_small + 3;
+    loglik_sparse_kernel<<<1, 1, 0, ctx->stream>>>(dev[0], dev[1], dev[2], dev[3], dev[4], n_obs, d_out);
+    CU(cudaGetLastError());
+    ++ctx->launches;
+    if (!out_dev) {
+        CU(cudaMemcpyAsync(logL, d_out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return HMX_OK;
+}
+
 int hmx_set_timing(hmx_ctx* ctx, int32_t enabled) {
     if (!ctx) return HMX_ERR_INVALID;
     ctx->timing = enabled != 0;

@@ -293,4 +293,22 @@ __global__ void wcov_final_kernel(const double* moments, const double* scatter, 
         for (int j = threadIdx.x; j < d; j += blockDim.x) mean_out[j] = mean[j];
 }
 
+// EV:305-334, rho = 0: strictly sequential accumulation in (row, species) order like the reference loop
+__global__ void loglik_sparse_kernel(const double* mu, const double* sig, const double* data, const double* sigma_obs,
+                                     const double* weights, int n_obs, double* out) {
+    double logL = 0.0;
+    for (int i = 0; i < n_obs; ++i) {
+        for (int j = 0; j < 5; ++j) {
+            const int e = i * 5 + j;
+            const double var_raw = sig[e] + sigma_obs[e] * sigma_obs[e];
+            const double v = (!(fabs(var_raw) <= 1.79e308) || var_raw <= 1e-20) ? 1e-20 : var_raw;
+            const double r = data[e] - mu[e];
+            const double w = weights ? weights[e] : 1.0;
+            logL -= w * 0.5 * log(2.0 * 3.14159265358979323846 * v);
+            logL -= w * 0.5 * (r * r) / v;
+        }
+    }
+    *out = logL;
+}
+
 }  // namespace hmx

@@ -165,6 +165,41 @@ class HamiltonEngine:
         self._check(self._lib.hmx_weighted_scatter(self._ctx, _addr(theta), _addr(w), N, d, _addr(mean), _addr(s)), "hmx_weighted_scatter")
         return s
 
+    # -- device-resident variants (CUDA torch tensors in, CUDA torch tensors out; scalars come back to the host) --
+    def weights_device(self, logL, delta_beta, out):
+        ls = C.c_double(0.0)
+        self._check(self._lib.hmx_weights(self._ctx, _addr(logL), logL.shape[0], delta_beta, _addr(out), C.addressof(ls)), "hmx_weights")
+        return ls.value
+
+    def resample_device(self, w, u, out_idx):
+        self._check(self._lib.hmx_resample(self._ctx, _addr(w), w.shape[0], float(u), _addr(out_idx)), "hmx_resample")
+
+    def weighted_moments_device(self, theta, w, out):
+        N, d = theta.shape
+        self._check(self._lib.hmx_weighted_moments(self._ctx, _addr(theta), _addr(w), N, d, _addr(out)), "hmx_weighted_moments")
+
+    def weighted_scatter_device(self, theta, w, mean, out):
+        N, d = theta.shape
+        self._check(self._lib.hmx_weighted_scatter(self._ctx, _addr(theta), _addr(w), N, d, _addr(mean), _addr(out)), "hmx_weighted_scatter")
+
+    def weighted_cov_device(self, theta, w, out_mean, out_cov):
+        N, d = theta.shape
+        self._check(self._lib.hmx_weighted_cov(self._ctx, _addr(theta), _addr(w), N, d, _addr(out_mean), _addr(out_cov)), "hmx_weighted_cov")
+
+    def log_likelihood_sparse(self, mu, sig, data, sigma_obs, weights=None) -> float:
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        n_obs = data.shape[0]
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        sig = np.ascontiguousarray(np.broadcast_to(np.asarray(sig, dtype=np.float64), data.shape))
+        so = np.ascontiguousarray(_abi.broadcast_sigma(sigma_obs, n_obs))
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        out = C.c_double(0.0)
+        self._check(
+            self._lib.hmx_log_likelihood_sparse(self._ctx, _addr(mu), _addr(sig), _addr(data), _addr(so), _addr(w), n_obs, C.addressof(out)),
+            "hmx_log_likelihood_sparse",
+        )
+        return out.value
+
     # -- measurement ------------------------------------------------------------------------------------
     def set_timing(self, enabled: bool = True):
         self._check(self._lib.hmx_set_timing(self._ctx, int(enabled)), "hmx_set_timing")

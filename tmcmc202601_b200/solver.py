@@ -1,0 +1,83 @@
+"""BiofilmNewtonSolver5S -- same constructor and methods as the reference class
+(tmcmc/program2602/improved_5species_jit.py:440-581), backed by hmx_trajectory_batch on a B200.
+
+    solver = BiofilmNewtonSolver5S(dt=1e-4, maxtimestep=2500, c_const=25.0, alpha_const=0.0,
+                                   phi_init=0.02, Kp1=1e-4, K_hill=0.05, n_hill=4.0)
+    t_arr, g_arr = solver.run_deterministic(theta)        # (T+1,), (T+1, 12)
+    g_batch = solver.run_deterministic_batch(theta[N,20]) # (N, T+1, 12)
+
+There is no NumPy/numba fallback: `use_numba` is accepted for signature compatibility and ignored.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import _abi
+from .engine import HamiltonEngine
+
+
+class BiofilmNewtonSolver5S:
+    THETA_NAMES = [
+        "a11", "a12", "a22", "b1", "b2", "a33", "a34", "a44", "b3", "b4",
+        "a13", "a14", "a23", "a24", "a55", "b5", "a15", "a25", "a35", "a45",
+    ]
+
+    def __init__(self, dt=1e-5, maxtimestep=500, eps=1e-6, Kp1=1e-4, eta_vec=None, eta_phi_vec=None,
+                 c_const=100.0, alpha_const=100.0, alpha_schedule=None, phi_init=0.2, active_species=None,
+                 use_numba=True, max_newton_iter=50, K_hill=0.0, n_hill=2.0, device=0):
+        if alpha_schedule is not None:
+            raise NotImplementedError("alpha_schedule belongs to the legacy 4-species pipeline (SURVEY 8(f)-4)")
+        self.dt, self.maxtimestep, self.eps, self.Kp1 = float(dt), int(maxtimestep), float(eps), float(Kp1)
+        self.c_const, self.alpha_const = float(c_const), float(alpha_const)
+        self.alpha_schedule = None
+        self.phi_init = _abi.broadcast_phi_init(phi_init)
+        self.max_newton_iter = int(max_newton_iter)
+        self.K_hill, self.n_hill = float(K_hill), float(n_hill)
+        self.active_species = [0, 1, 2, 3, 4] if active_species is None else list(active_species)
+        self.Eta_vec = np.ones(5) if eta_vec is None else np.asarray(eta_vec, dtype=float)
+        self.Eta_phi_vec = np.ones(5) if eta_phi_vec is None else np.asarray(eta_phi_vec, dtype=float)
+        self.use_numba = False  # nothing is JIT-compiled here; kept for attribute compatibility
+        self.device = int(device)
+        self._engine = None
+
+    def solver_kwargs(self) -> dict:
+        return dict(dt=self.dt, maxtimestep=self.maxtimestep, eps=self.eps, Kp1=self.Kp1, eta_vec=self.Eta_vec,
+                    eta_phi_vec=self.Eta_phi_vec, c_const=self.c_const, alpha_const=self.alpha_const,
+                    max_newton_iter=self.max_newton_iter, K_hill=self.K_hill, n_hill=self.n_hill,
+                    active_species=self.active_species)
+
+    def _eng(self) -> HamiltonEngine:
+        if self._engine is None:
+            # a trajectory-only context: one dummy condition carrying the initial state, no observation rows
+            cond = _abi.make_cond(np.zeros((0, 5)), [], 1.0, self.phi_init, tsm_variance=False)
+            self._engine = HamiltonEngine(_abi.make_config([cond], **self.solver_kwargs()), device=self.device)
+        return self._engine
+
+    def theta_to_matrices(self, theta):
+        """theta (20,) -> symmetric A (5,5), b (5,).  Index map of S5:513-559 (pure indexing, host side)."""
+        theta = np.asarray(theta)
+        A = np.zeros((5, 5), dtype=theta.dtype)
+        b = np.zeros(5, dtype=theta.dtype)
+        pairs = {0: (0, 0), 1: (0, 1), 2: (1, 1), 5: (2, 2), 6: (2, 3), 7: (3, 3), 10: (0, 2), 11: (0, 3),
+                 12: (1, 2), 13: (1, 3), 14: (4, 4), 16: (0, 4), 17: (1, 4), 18: (2, 4), 19: (3, 4)}
+        for k, (i, j) in pairs.items():
+            A[i, j] = theta[k]
+            A[j, i] = theta[k]
+        for k, i in {3: 0, 4: 1, 8: 2, 9: 3, 15: 4}.items():
+            b[i] = theta[k]
+        return A, b
+
+    def run_deterministic_batch(self, theta):
+        theta = np.ascontiguousarray(np.atleast_2d(np.real(theta)), dtype=np.float64)
+        g, _, _ = self._eng().trajectory_batch(theta[:, :20])
+        return g
+
+    def run_deterministic(self, theta):
+        g = self.run_deterministic_batch(np.asarray(theta, dtype=np.float64)[None, :])[0]
+        t_arr = np.empty(self.maxtimestep + 1)
+        t_arr[0] = 0.0
+        t_arr[1:] = (np.arange(self.maxtimestep) + 1) * self.dt  # tt = (step + 1) * dt, S5:860
+        return t_arr, g
+
+    solve = run_deterministic  # alias used by the TSM wrapper (S5:646)
