@@ -80,7 +80,7 @@ def test_weighted_cov_matches_numpy(eng, N, d):
     mean, cov = eng.weighted_cov(theta, w)
     ref = np.atleast_2d(np.cov(theta.T, aweights=w))
     assert np.allclose(cov, ref, rtol=1e-11, atol=1e-14 * np.abs(ref).max())
-    assert np.allclose(cov, cov.T, rtol=0, atol=1e-18) and np.allclose(mean, np.average(theta, axis=0, weights=w), rtol=1e-13)
+    assert np.array_equal(cov, cov.T) and np.allclose(mean, np.average(theta, axis=0, weights=w), rtol=1e-13)
     # the two shard-local halves (multi-GPU path) reproduce it
     half = N // 2
     mom = eng.weighted_moments(theta[:half], w[:half]) + eng.weighted_moments(theta[half:], w[half:]) if half else eng.weighted_moments(theta, w)

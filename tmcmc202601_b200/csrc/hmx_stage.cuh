@@ -262,7 +262,9 @@ __global__ void __launch_bounds__(kRedThreads) wscatter_kernel(const double* __r
         for (int q = 0; q < 4; ++q) {
             const int e = threadIdx.x + q * blockDim.x;
             if (q < per && e < dd) {
-                const int a = e / d, b = e % d;
+                // canonical operand order so that entry (a,b) and its mirror (b,a) round identically
+                const int r0 = e / d, c0 = e % d;
+                const int a = r0 < c0 ? r0 : c0, b = r0 < c0 ? c0 : r0;
                 double s = acc[q];
                 for (int i = 0; i < n; ++i) s = fma(xs[i * d + a], xs[i * d + b] * ws[i], s);
                 acc[q] = s;
