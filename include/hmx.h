@@ -14,8 +14,9 @@
  *   - plain C, no exceptions: every call returns 0 on success or a negative hmx_status; the message is
  *     available from hmx_last_error().
  *   - every array argument is caller-owned and may be a HOST pointer (pageable or pinned) or a DEVICE
- *     pointer on the context's GPU (detected with cudaPointerGetAttributes).  Host inputs are staged
- *     through pinned buffers owned by the context; a call with any host OUTPUT pointer returns after the
+ *     pointer on the context's GPU (detected with cudaPointerGetAttributes).  Host inputs are copied into
+ *     device buffers owned by the context (cudaMemcpyAsync on the context stream; pass pinned memory for
+ *     full PCIe rate); a call with any host OUTPUT pointer returns after the
  *     results have landed (stream-synchronised); a call whose outputs are all device pointers only
  *     enqueues work on the context stream (hmx_set_stream / hmx_synchronize).
  *   - one context per process and GPU; calls on one context serialise (not thread-safe, like the
