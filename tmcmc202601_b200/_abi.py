@@ -186,12 +186,15 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    import os
+
+    lib_path = Path(os.environ.get("HMX_LIB", str(LIB_PATH)))  # HMX_LIB: kernel-variant experiments only
+    if not lib_path.exists():
         raise RuntimeError(
-            f"{LIB_PATH} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; "
+            f"{lib_path} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; "
             "g.build()').  This package has no CPU fallback."
         )
-    lib = C.CDLL(str(LIB_PATH))
+    lib = C.CDLL(str(lib_path))
     dp, ip, up, lp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_int64)
     vp = C.c_void_p
     lib.hmx_create.argtypes = [C.POINTER(vp), C.POINTER(HmxConfig), C.c_int32]

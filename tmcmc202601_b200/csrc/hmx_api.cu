@@ -53,9 +53,10 @@ struct hmx_ctx {
 
     // device scratch
     DevBuf theta, cond_id, pairs, status, iters, trips, logL, obs_state, traj;
-    DevBuf st_in0, st_in1, st_in2, st_out0, st_out1, partial, cs;
+    DevBuf st_in0, st_in1, st_in2, st_out0, st_out1, partial, cs, order;
+    SchedState* d_sched = nullptr;
     CondConsts* d_cond = nullptr;
-    unsigned long long* d_counters = nullptr;  // [0] work counter, [1] sum iters, [2] sum trips
+    unsigned long long* d_counters = nullptr;  // [0] work counter, [1] sum iters, [2] sum trips, [4..12) trips per condition, [12..20) evaluations per condition
     StageState* d_stage = nullptr;
     unsigned int* d_tickets = nullptr;  // [64]
     double* d_small = nullptr;          // [2048] moments / mean / scatter / small outputs
@@ -217,6 +218,21 @@ int run_chunk(hmx_ctx* ctx, const double* d_theta, const int32_t* d_cond, long l
     P.trips = (uint32_t*)ctx->trips.p;
     P.work_counter = ctx->d_counters;
     P.totals = ctx->d_counters + 1;
+    P.cond_trips = ctx->d_counters + 4;
+    P.cond_evals = ctx->d_counters + 12;
+    P.order = nullptr;
+    P.n_cond = ctx->cfg.n_cond;
+    if (d_cond && ctx->cfg.n_cond > 1 && N < (1ll << 31)) {
+        // expensive conditions first (see SchedState); three tiny launches, no host synchronisation
+        if ((rc = ensure(ctx, ctx->order, (size_t)N * sizeof(int)))) return rc;
+        const int sb = red_blocks(N);
+        sched_hist_kernel<<<sb, kRedThreads, 0, ctx->stream>>>(d_cond, N, ctx->d_sched, ctx->cfg.n_cond);
+        sched_plan_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_sched, ctx->cfg.n_cond);
+        sched_scatter_kernel<<<sb, kRedThreads, 0, ctx->stream>>>(d_cond, N, ctx->d_sched, (int*)ctx->order.p, ctx->cfg.n_cond);
+        CU(cudaGetLastError());
+        ctx->launches += 3;
+        P.order = (const int*)ctx->order.p;
+    }
 
     const long long want_blocks = (N + kOdeThreads - 1) / kOdeThreads;
     const int blocks = (int)std::min<long long>(want_blocks, (long long)ctx->sm_count * ctx->ode_blocks_per_sm);
@@ -228,6 +244,9 @@ int run_chunk(hmx_ctx* ctx, const double* d_theta, const int32_t* d_cond, long l
         CU(cudaEventRecord(ctx->ev1, ctx->stream));
         ctx->timing_pending = true;
     }
+    sched_update_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_sched, ctx->d_counters + 4, ctx->d_counters + 12, ctx->cfg.n_cond);
+    CU(cudaGetLastError());
+    ++ctx->launches;
 
     if (want_logL) {
         ObsParams O;
@@ -245,6 +264,7 @@ int run_chunk(hmx_ctx* ctx, const double* d_theta, const int32_t* d_cond, long l
         O.logL = d_logL;
         O.obs_state = d_obs_state;
         O.obs_stride = (long long)std::max(ctx->n_obs_max, 1) * 12;
+        O.n_cond = ctx->cfg.n_cond;
         const int ob = (int)((N + 127) / 128);
         HMX_DISPATCH(launch_obs, ctx, O, ob);
         CU(cudaGetLastError());
@@ -354,8 +374,10 @@ int hmx_create(hmx_ctx** out, const hmx_config* cfg, int32_t device) {
     ctx->stream = ctx->own_stream;
     CU_CREATE(cudaMalloc((void**)&ctx->d_cond, sizeof(CondConsts) * HMX_MAX_COND));
     CU_CREATE(cudaMemcpy(ctx->d_cond, ctx->C, sizeof(CondConsts) * HMX_MAX_COND, cudaMemcpyHostToDevice));
-    CU_CREATE(cudaMalloc((void**)&ctx->d_counters, 4 * sizeof(unsigned long long)));
-    CU_CREATE(cudaMemset(ctx->d_counters, 0, 4 * sizeof(unsigned long long)));
+    CU_CREATE(cudaMalloc((void**)&ctx->d_counters, 20 * sizeof(unsigned long long)));
+    CU_CREATE(cudaMemset(ctx->d_counters, 0, 20 * sizeof(unsigned long long)));
+    CU_CREATE(cudaMalloc((void**)&ctx->d_sched, sizeof(SchedState)));
+    CU_CREATE(cudaMemset(ctx->d_sched, 0, sizeof(SchedState)));
     CU_CREATE(cudaMalloc((void**)&ctx->d_stage, sizeof(StageState)));
     CU_CREATE(cudaMemset(ctx->d_stage, 0, sizeof(StageState)));
     CU_CREATE(cudaMalloc((void**)&ctx->d_tickets, 64 * sizeof(unsigned int)));
@@ -374,11 +396,12 @@ void hmx_destroy(hmx_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->theta, &ctx->cond_id, &ctx->pairs, &ctx->status, &ctx->iters, &ctx->trips, &ctx->logL,
                       &ctx->obs_state, &ctx->traj, &ctx->st_in0, &ctx->st_in1, &ctx->st_in2, &ctx->st_out0, &ctx->st_out1,
-                      &ctx->partial, &ctx->cs};
+                      &ctx->partial, &ctx->cs, &ctx->order};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->d_cond) cudaFree(ctx->d_cond);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_sched) cudaFree(ctx->d_sched);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->d_tickets) cudaFree(ctx->d_tickets);
     if (ctx->d_small) cudaFree(ctx->d_small);

@@ -60,6 +60,7 @@ inline void make_solver_consts(const hmx_config& c, SolverConsts& K) {
         K.inv_eta[i] = 1.0 / c.eta[i];
         K.c_eta[i] = c.c_const / c.eta[i];
         K.alpha_eta[i] = c.alpha_const / c.eta[i];
+        K.etaphi_eta[i] = c.eta_phi[i] / c.eta[i];
     }
     K.n_steps = c.n_steps;
     K.max_iter = c.max_newton_iter;

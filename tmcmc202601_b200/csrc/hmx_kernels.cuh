@@ -21,8 +21,20 @@
 
 namespace hmx {
 
-constexpr int kOdeThreads = 128;  // 4 warps: one per SM sub-partition
-constexpr int kOdeMinBlocks = 2;  // -> 255 registers / thread available, 8 warps / SM
+#ifndef HMX_ODE_THREADS
+#define HMX_ODE_THREADS 128
+#endif
+#ifndef HMX_ODE_MINBLOCKS
+#define HMX_ODE_MINBLOCKS 2
+#endif
+constexpr int kOdeThreads = HMX_ODE_THREADS;      // 4 warps: one per SM sub-partition
+constexpr int kOdeMinBlocks = HMX_ODE_MINBLOCKS;  // 2 -> 255 registers / thread available, 8 warps / SM
+
+// cond_id values outside [0, n_cond) are treated as condition 0 (the C ABI documents the valid range)
+__device__ __forceinline__ int cond_index(const int32_t* cond_id, long long i, int n_cond) {
+    const int c = cond_id ? cond_id[i] : 0;
+    return ((unsigned)c < (unsigned)n_cond) ? c : 0;
+}
 
 struct OdeCond {
     double g0[12];
@@ -45,14 +57,19 @@ struct OdeParams {
     uint32_t* trips;         // [N]
     unsigned long long* work_counter;  // zeroed before launch
     unsigned long long* totals;        // [2] += sum iters, sum trips
+    unsigned long long* cond_trips;    // [HMX_MAX_COND] += residual evaluations per condition (cost model of the scheduler)
+    unsigned long long* cond_evals;    // [HMX_MAX_COND] += evaluations per condition
+    const int* order;                  // [N] work position -> evaluation index (most expensive condition first), or null
+    int n_cond;
 };
 
 template <bool ALPHA, int HILL>
 __global__ void __launch_bounds__(kOdeThreads, kOdeMinBlocks) ode_kernel(const __grid_constant__ OdeParams P) {
     const long long nthreads = (long long)gridDim.x * blockDim.x;
-    long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    while (w < P.N) {
-        const int c = P.cond_id ? P.cond_id[w] : 0;
+    long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    while (pos < P.N) {
+        const long long w = P.order ? (long long)P.order[pos] : pos;
+        const int c = cond_index(P.cond_id, w, P.n_cond);
         const OdeCond& oc = P.cond[c];
         Lane s;
         {
@@ -101,7 +118,83 @@ __global__ void __launch_bounds__(kOdeThreads, kOdeMinBlocks) ode_kernel(const _
         P.trips[w] = s.trips;
         atomicAdd(P.totals + 0, (unsigned long long)s.iters);
         atomicAdd(P.totals + 1, (unsigned long long)s.trips);
-        w = (long long)atomicAdd(P.work_counter, 1ULL) + nthreads;
+        atomicAdd(P.cond_trips + c, (unsigned long long)s.trips);
+        atomicAdd(P.cond_evals + c, 1ULL);
+        pos = (long long)atomicAdd(P.work_counter, 1ULL) + nthreads;
+    }
+}
+
+// ---- cost-ordered work list ---------------------------------------------------------------------------
+// Evaluation cost is data dependent (9k-34k residual evaluations) and differs systematically between
+// conditions (means 13k-23k on the synthetic prior workload).  Lanes fetch work dynamically, so the kernel's
+// tail is about one evaluation long; handing out the expensive condition first shortens it.  The expected
+// cost per condition is an exponential moving average of the previous launches' own counters, kept on the
+// device (no host synchronisation); the first launch of a context uses the input order.
+struct SchedState {
+    double ema_trips[HMX_MAX_COND];      // expected residual evaluations per evaluation, 0 = unknown
+    unsigned int count[HMX_MAX_COND];    // histogram of the current batch
+    unsigned int cursor[HMX_MAX_COND];   // scatter cursors
+    unsigned int offset[HMX_MAX_COND];
+    int use_order;                       // 0 -> identity order (no cost information yet, or a single condition)
+};
+
+__global__ void sched_hist_kernel(const int32_t* __restrict__ cond_id, long long N, SchedState* st, int n_cond) {
+    __shared__ unsigned int h[HMX_MAX_COND];
+    if (threadIdx.x < HMX_MAX_COND) h[threadIdx.x] = 0u;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
+        atomicAdd(&h[cond_index(cond_id, i, n_cond)], 1u);
+    __syncthreads();
+    if (threadIdx.x < HMX_MAX_COND && h[threadIdx.x]) atomicAdd(&st->count[threadIdx.x], h[threadIdx.x]);
+}
+
+__global__ void sched_plan_kernel(SchedState* st, int n_cond) {
+    int rank[HMX_MAX_COND];
+    int known = 0, used = 0;
+    for (int c = 0; c < n_cond; ++c) {
+        rank[c] = c;
+        if (st->count[c]) {
+            ++used;
+            if (st->ema_trips[c] > 0.0) ++known;
+        }
+    }
+    st->use_order = (used > 1 && known == used) ? 1 : 0;
+    for (int a = 1; a < n_cond; ++a)  // insertion sort by expected cost, descending
+        for (int b = a; b > 0 && st->ema_trips[rank[b]] > st->ema_trips[rank[b - 1]]; --b) {
+            const int t = rank[b];
+            rank[b] = rank[b - 1];
+            rank[b - 1] = t;
+        }
+    unsigned int off = 0;
+    for (int k = 0; k < n_cond; ++k) {
+        st->offset[rank[k]] = off;
+        off += st->count[rank[k]];
+        st->cursor[rank[k]] = 0u;
+    }
+}
+
+__global__ void sched_scatter_kernel(const int32_t* __restrict__ cond_id, long long N, SchedState* st, int* __restrict__ order, int n_cond) {
+    const bool use = st->use_order != 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        if (use) {
+            const int c = cond_index(cond_id, i, n_cond);
+            order[st->offset[c] + atomicAdd(&st->cursor[c], 1u)] = (int)i;
+        } else {
+            order[i] = (int)i;
+        }
+    }
+}
+
+// after the ODE kernel: fold this launch's per-condition cost into the moving average, re-arm the accumulators
+__global__ void sched_update_kernel(SchedState* st, unsigned long long* cond_trips, unsigned long long* cond_evals, int n_cond) {
+    for (int c = 0; c < n_cond; ++c) {
+        if (cond_evals[c]) {
+            const double m = (double)cond_trips[c] / (double)cond_evals[c];
+            st->ema_trips[c] = st->ema_trips[c] > 0.0 ? 0.5 * (st->ema_trips[c] + m) : m;
+        }
+        cond_trips[c] = 0ull;
+        cond_evals[c] = 0ull;
+        st->count[c] = 0u;
     }
 }
 
@@ -119,13 +212,14 @@ struct ObsParams {
     double* logL;
     double* obs_state;     // [N, n_obs_max, 12] or null
     long long obs_stride;  // n_obs_max * 12
+    int n_cond;
 };
 
 template <bool ALPHA, int HILL>
 __global__ void __launch_bounds__(128) obs_kernel(const __grid_constant__ ObsParams P) {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= P.N) return;
-    const int c = P.cond_id ? P.cond_id[w] : 0;
+    const int c = cond_index(P.cond_id, w, P.n_cond);
     const CondConsts& C = P.cond[c];
     double th[HMX_NTHETA];
 #pragma unroll

@@ -48,6 +48,7 @@ constexpr double kClipHi = 1.0 - 1e-12;   // S5:68
 struct SolverConsts {
     double dt, inv_dt, eps, Kp1, c, alpha, K_hill, n_hill, Kn;  // Kn = K_hill^n_hill
     double eta[5], eta_phi[5], inv_eta[5], c_eta[5], alpha_eta[5];  // c/eta_i, alpha/eta_i
+    double etaphi_eta[5];  // eta_phi_i / eta_i: lets (1/eta)(eta_phi + eta psi^2) be one fma
     int32_t n_steps, max_iter;
     int32_t hill_mode;  // 0 off, 1..4 integer exponent, 5 generic pow
     int32_t pad_;
@@ -178,8 +179,8 @@ HMX_HD void residual(const SolverConsts& K, const double (&x)[12], const double 
     for (int i = 0; i < 5; ++i) {
         const double v = e.ph[i], u = e.ps[i];
         // Q_i, S5:98-106
-        const double t2 = K.inv_eta[i] * (gam + fma(fma(K.eta[i] * u, u, K.eta_phi[i]), e.phd[i],
-                                                     K.eta[i] * e.p[i] * e.psd[i]));
+        // (1/eta)[gamma + (eta_phi + eta psi^2) phidot + eta phi psi psidot], with 1/eta distributed
+        const double t2 = fma(K.inv_eta[i], gam, fma(fma(u, u, K.etaphi_eta[i]), e.phd[i], e.p[i] * e.psd[i]));
         const double qi = e.fph[i] + t2 - K.c_eta[i] * u * e.I[i];
         // Q_{6+i}, S5:116-123
         double qs = e.fps[i] + fma(e.p[i], e.phd[i], v * v * e.psd[i]) - K.c_eta[i] * v * e.I[i];
@@ -291,7 +292,7 @@ HMX_HD void direction(const SolverConsts& K, const Eval& e, const double (&A)[15
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
         const double v = e.ph[i], u = e.ps[i], pd = e.phd[i], sd = e.psd[i];
-        const double ce = K.c_eta[i], eta = K.eta[i];
+        const double ce = K.c_eta[i];
         const double sv = fma(2.0, v, -1.0);
         const double phi_p = -e.fph[i] * fma(3.0 * sv, e.rph[i], 2.0);                                  // S5:185-187
         const double wu = fma(u, u, -u);
@@ -300,10 +301,8 @@ HMX_HD void direction(const SolverConsts& K, const Eval& e, const double (&A)[15
         const double aii = hrow[i] * A[apk(i, i)];
         const double ap = aii * e.p[i];
         // 2x2 diagonal block of species i (rows i, 6+i; columns i, 6+i), S5:199-245 (+ S5:254-271)
-        const double d00 = phi_p + K.inv_eta[i] * fma(fma(eta * u, u, K.eta_phi[i]), K.inv_dt, eta * u * sd) -
-                           ce * u * fma(2.0 * aii, u, e.I[i]);
-        const double d01 = K.inv_eta[i] * (eta * fma(2.0 * u, pd, fma(v, sd, e.p[i] * K.inv_dt))) -
-                           ce * fma(3.0, ap, e.I[i]);
+        const double d00 = phi_p + fma(fma(u, u, K.etaphi_eta[i]), K.inv_dt, u * sd) - ce * u * fma(2.0 * aii, u, e.I[i]);
+        const double d01 = fma(2.0 * u, pd, fma(v, sd, e.p[i] * K.inv_dt)) - ce * fma(3.0, ap, e.I[i]);  // (1/eta) eta = 1
         const double d10 = fma(u, pd, fma(e.p[i], K.inv_dt, 2.0 * v * sd)) - ce * fma(3.0, ap, 2.0 * e.I[i]);
         double d11 = psi_p + fma(v, pd, v * v * K.inv_dt) - 2.0 * ce * aii * v * v;
         if (ALPHA) d11 += b[i] * K.alpha_eta[i];
@@ -314,8 +313,9 @@ HMX_HD void direction(const SolverConsts& K, const Eval& e, const double (&A)[15
         const double r0 = -e.Q[i], r1 = -e.Q[6 + i];
         a0[i] = fma(d11, r0, -d01 * r1) * rdet;
         a1[i] = fma(d00, r1, -d10 * r0) * rdet;
-        b0[i] = (d11 * K.inv_eta[i]) * rdet;  // u_i = (1/eta_i, 0): S5:220
-        b1[i] = (-d10 * K.inv_eta[i]) * rdet;
+        const double rdi = rdet * K.inv_eta[i];  // u_i = (1/eta_i, 0): S5:220
+        b0[i] = d11 * rdi;
+        b1[i] = -d10 * rdi;
         d0[i] = fma(d11, u, -d01 * v) * rdet;
         d1[i] = fma(d00, v, -d10 * u) * rdet;
     }
