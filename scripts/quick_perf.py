@@ -7,14 +7,20 @@ from tmcmc202601_b200 import workloads
 from tmcmc202601_b200.engine import HamiltonEngine
 
 def main():
-    sizes = [int(x) for x in sys.argv[1:]] or [250, 1250, 9472]
-    wl0 = workloads.four_condition_workload(8)
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    solver = dict(workloads.T500_SOLVER, K_hill=0.05, n_hill=4.0) if "--t500" in sys.argv else None
+    sizes = [int(x) for x in args] or [250, 1250, 9472]
+    wl0 = workloads.four_condition_workload(8, solver=solver)
+    if solver is not None:  # observation rows rescaled onto the 500-step grid
+        for k in range(4):
+            for o in range(5):
+                wl0.config.cond[k].idx_sparse[o] = [68, 136, 226, 339, 475][o]
     eng = HamiltonEngine(wl0.config, 0)
     print("fp64 peak TFLOP/s:", eng.measure_fp64_peak())
     eng.set_timing(True)
     for n in sizes:
-        wl = workloads.four_condition_workload(n)
-        for rep in range(2):
+        wl = workloads.four_condition_workload(n, solver=solver)
+        for rep in range(3):
             t0 = time.perf_counter()
             logL, st, it = eng.loglik_batch(wl.theta, wl.cond_id, return_status=True)
             t1 = time.perf_counter()

@@ -99,14 +99,14 @@ int emu_validate(const hmx_config* cfg) {
 
 // the two 5x5 solvers of hmx_model.cuh on a caller-supplied system M[5][7]; returns the smallest pivot
 double emu_solve5x2(const double* M, double* X, int pivoted) {
-    if (pivoted) {
+    if (pivoted == 1) {
         solve5x2_pivoted(M, X);
         return 0.0;
     }
     double S[5][7];
     for (int r = 0; r < 5; ++r)
         for (int c = 0; c < 7; ++c) S[r][c] = M[r * 7 + c];
-    const double pmin = solve5x2_natural(S);
+    const double pmin = (pivoted == 2) ? solve5x2_block23(S) : solve5x2_natural(S);
     for (int r = 0; r < 5; ++r) {
         X[r] = S[r][5];
         X[5 + r] = S[r][6];

@@ -225,6 +225,18 @@ def main():
     )
     manifest["toy_tmcmc"] = {"stages": len(ss), "final_beta": res.beta_schedule[-1], "log_evidence": res.log_evidence}
 
+    # ------------------------------------------------------------------ posterior summaries of the stored production run
+    # _runs/Dysbiotic_HOBIC_K0.05_n4.0_1k30: N=1000, 2 chains, seed 42, 63 h on 8 CPU processes (results_summary.json)
+    s_ref = np.load(legacy_dir / "samples.npy")
+    l_ref = np.load(legacy_dir / "logL.npy")
+    np.savez_compressed(
+        OUT / "posterior_dh_1k30.npz", n=s_ref.shape[0], mean=s_ref.mean(0), std=s_ref.std(0, ddof=1),
+        q=np.quantile(s_ref, [0.05, 0.25, 0.5, 0.75, 0.95], axis=0), logL_mean=l_ref.mean(), logL_std=l_ref.std(),
+        logL_max=l_ref.max(), logL_min=l_ref.min(), MAP=s_ref[np.argmax(l_ref)],
+        chain_means=np.stack([s_ref[:1000].mean(0), s_ref[1000:].mean(0)]),
+    )
+    manifest["production_run"] = {"samples": list(s_ref.shape), "logL_max": float(l_ref.max()), "elapsed_s": 226864.8}
+
     manifest["wall_s"] = round(time.time() - t_start, 1)
     (OUT / "MANIFEST.json").write_text(json.dumps(manifest, indent=1))
     print(json.dumps(manifest, indent=1))

@@ -47,3 +47,23 @@ def test_short_real_tmcmc_run(built):
     ev = make_evaluator(theta_base)
     prior_ll = ev.batch(workloads.sample_prior(cd["bounds"], 256, np.random.default_rng(0)))
     assert logL[0].mean() > np.median(prior_ll)
+
+
+def test_production_run_posterior_matches_reference_run(built):
+    """BASELINE.json configs[1]: the stored production run (_runs/Dysbiotic_HOBIC_K0.05_n4.0_1k30, N=1000, 2 chains,
+    seed 42, K=5; 63 h on the reference) re-run through the drop-in API; posterior summaries must agree with the
+    reference's samples within Monte-Carlo error (tests/golden/posterior_dh_1k30.npz)."""
+    import sys
+
+    sys.path.insert(0, str(GOLDEN.parents[1] / "scripts"))
+    import run_production_tmcmc as rp
+
+    out, samples, ll = rp.run_condition("Dysbiotic_HOBIC_legacy_1k30", 1000, 2)
+    cmp_ = rp.compare_with_reference(samples, ll)
+    print(f"wall {out['wall_s']:.2f} s for {out['likelihood_evaluations']} evaluations; {cmp_}")
+    assert all(out["converged"]) and samples.shape == (2000, 20)
+    assert cmp_["z_mean_max"] < 4.5  # 20 parameters, n_eff ~ 200 on both sides
+    assert 0.75 < cmp_["std_ratio_min"] and cmp_["std_ratio_max"] < 1.33
+    assert cmp_["quantile_shift_over_std_max"] < 0.5
+    assert abs(out["logL_max"] - cmp_["logL_max_ref"]) < 1.5 and abs(out["logL_mean"] - cmp_["logL_mean_ref"]) < 0.5
+    assert out["wall_s"] < 120.0

@@ -77,21 +77,36 @@ def test_solve5x2_natural_and_pivoted_agree_with_numpy():
         rhs = rng.normal(size=(5, 2))
         M = np.ascontiguousarray(np.hstack([S, rhs]))
         ref = np.linalg.solve(S, rhs)
-        for pivoted in (1, 0):
+        for mode in (1, 0, 2):  # pivoted, natural-order LU, 2+3 block elimination (the kernel's fast path)
             X = np.zeros(10)
-            pmin = emu.emu_solve5x2(dptr(M), dptr(X), pivoted)
+            health = emu.emu_solve5x2(dptr(M), dptr(X), mode)
             assert np.allclose(X.reshape(2, 5).T, ref, rtol=1e-12, atol=1e-14)
-        assert pmin > _abi_floor()  # natural order (last call) reports a healthy pivot
+            assert mode == 1 or health > _abi_floor()  # fast paths report a healthy system
     # a system the natural order cannot handle (zero leading pivot): the guard must trip, the pivoted path solves it
     S = np.eye(5)[[1, 0, 2, 3, 4]] + 0.01 * rng.normal(size=(5, 5))
     S[0, 0] = 0.0
     rhs = rng.normal(size=(5, 2))
     M = np.ascontiguousarray(np.hstack([S, rhs]))
     X = np.zeros(10)
-    pmin = emu.emu_solve5x2(dptr(M), dptr(X), 0)
-    assert not (pmin >= _abi_floor())
+    assert not (emu.emu_solve5x2(dptr(M), dptr(X), 0) >= _abi_floor())
     emu.emu_solve5x2(dptr(M), dptr(X), 1)
     assert np.allclose(X.reshape(2, 5).T, np.linalg.solve(S, rhs), rtol=1e-11, atol=1e-13)
+    # the 2+3 block path inverts the leading 2x2 block explicitly, so a row swap inside it is harmless ...
+    assert emu.emu_solve5x2(dptr(M), dptr(X), 2) >= _abi_floor()
+    assert np.allclose(X.reshape(2, 5).T, np.linalg.solve(S, rhs), rtol=1e-11, atol=1e-13)
+    # ... but a (near-)singular leading block or Schur complement must trip its guard
+    S2 = np.eye(5) + 0.01 * rng.normal(size=(5, 5))
+    S2[1, :2] = S2[0, :2] * (1 + 1e-9)
+    M2 = np.ascontiguousarray(np.hstack([S2, rhs]))
+    assert not (emu.emu_solve5x2(dptr(M2), dptr(X), 2) >= _abi_floor())
+    emu.emu_solve5x2(dptr(M2), dptr(X), 1)
+    assert np.allclose(X.reshape(2, 5).T, np.linalg.solve(S2, rhs), rtol=1e-9, atol=1e-11)
+    S3 = np.eye(5) + 0.01 * rng.normal(size=(5, 5))
+    S3[4, 2:] = S3[3, 2:]
+    S3[4, :2] = S3[3, :2]
+    S3[4, 4] += 1e-3  # rows 3 and 4 almost identical: det T' ~ 1e-3
+    M3 = np.ascontiguousarray(np.hstack([S3, rhs]))
+    assert not (emu.emu_solve5x2(dptr(M3), dptr(X), 2) >= _abi_floor())
 
 
 def _abi_floor():

@@ -72,6 +72,11 @@ __global__ void __launch_bounds__(kOdeThreads, kOdeMinBlocks) ode_kernel(const _
         const int c = cond_index(P.cond_id, w, P.n_cond);
         const OdeCond& oc = P.cond[c];
         Lane s;
+#if defined(HMX_A_IN_SMEM)
+        __shared__ double smA[15 * kOdeThreads];
+        static_assert(HMX_A_IN_SMEM == kOdeThreads, "HMX_A_IN_SMEM must equal the ODE block size");
+        s.A.p = smA + threadIdx.x;
+#endif
         {
             double th[HMX_NTHETA];
             const double* tp = P.theta + w * HMX_NTHETA;

@@ -29,11 +29,21 @@ enum : int32_t { kModeEval = 0, kModeTrial = 1 };
 
 constexpr uint32_t kStNonfinite = 1u, kStMaxIter = 2u, kStSingular = 4u;  // == HMX_ST_* in include/hmx.h
 
+#if defined(HMX_A_IN_SMEM) && defined(__CUDACC__)
+using LaneA = SmemCol<HMX_A_IN_SMEM>;  // interaction matrix parked in shared memory (30 registers freed)
+#else
+struct LaneA {
+    double v[15];
+    HMX_HD double& operator[](int k) { return v[k]; }
+    HMX_HD const double& operator[](int k) const { return v[k]; }
+};
+#endif
+
 struct Lane {
     double gp[11];   // previous time level: phi(5), phi_0, psi(5)
     double g[12];    // current Newton iterate
     double d[12];    // current Newton direction
-    double A[15];    // packed symmetric interaction matrix
+    LaneA A;         // packed symmetric interaction matrix
     double b[5];     // decay vector (only read when alpha != 0)
     double normQ;    // ||Q||_inf at the iterate
     double step;     // current line-search step length

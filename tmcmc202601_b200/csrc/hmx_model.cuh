@@ -64,8 +64,18 @@ HMX_HD constexpr int apk(int i, int j) {
     return (i <= j) ? (i * 5 - (i * (i - 1)) / 2 + (j - i)) : (j * 5 - (j * (j - 1)) / 2 + (i - j));
 }
 
+// Column of a [k][thread] array in shared memory: element k of this thread lives at p[k * STRIDE]
+// (consecutive threads -> consecutive 8-byte words: conflict-free).  Used to park per-lane data that is
+// read a few times per trip (the interaction matrix) outside the register file.
+template <int STRIDE>
+struct SmemCol {
+    double* p;
+    HMX_HD double& operator[](int k) const { return p[k * STRIDE]; }
+};
+
 // theta (20) -> packed symmetric A (15) and b (5): S5:513-559
-HMX_HD void theta_to_Ab(const double* th, double (&A)[15], double (&b)[5]) {
+template <class AT>
+HMX_HD void theta_to_Ab(const double* th, AT& A, double (&b)[5]) {
 #pragma unroll
     for (int k = 0; k < 15; ++k) A[k] = 0.0;
     A[apk(0, 0)] = th[0];
@@ -123,9 +133,9 @@ struct Eval {
 };
 
 // Residual Q at the candidate x (S5:43-127).  gp = [phi_old(5), phi0_old, psi_old(5)].
-template <bool ALPHA, int HILL>
+template <bool ALPHA, int HILL, class AT>
 HMX_HD void residual(const SolverConsts& K, const double (&x)[12], const double (&gp)[11],
-                     const double (&A)[15], const double (&b)[5], Eval& e) {
+                     const AT& A, const double (&b)[5], Eval& e) {
     const double gam = x[11];
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
@@ -236,6 +246,54 @@ HMX_HD double solve5x2_natural(double (&S)[5][7]) {
     return pmin;  // NaN-safe: fmin ignores NaN pivots, the caller also checks the direction for finiteness
 }
 
+// Same system by 2+3 block elimination: explicit 2x2 inverse, Schur complement, 3x3 adjugate.  Only two
+// reciprocals sit on the dependency chain (five in the natural-order LU) and every other level is a batch of
+// independent FMAs, which is what a latency-bound FP64 kernel with two warps per scheduler needs.
+// Returns min(|det P|, |det T'|): both are 1 + O(|g C|) for a healthy system.
+HMX_HD double solve5x2_block23(double (&S)[5][7]) {
+    const double tp = S[0][1] * S[1][0];
+    const double detP = fma(S[0][0], S[1][1], -tp) + fma(-S[0][1], S[1][0], tp);
+    const double rP = 1.0 / detP;
+    const double i00 = S[1][1] * rP, i01 = -S[0][1] * rP, i10 = -S[1][0] * rP, i11 = S[0][0] * rP;
+    double X[2][5];  // P^{-1} [Q | r_top]: columns 0..2 = Q, 3..4 = right-hand sides
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        const double q0 = S[0][2 + c], q1 = S[1][2 + c];
+        X[0][c] = fma(i00, q0, i01 * q1);
+        X[1][c] = fma(i10, q0, i11 * q1);
+    }
+    double T[3][5];  // Schur complement and reduced right-hand sides
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 5; ++c) T[r][c] = fma(-S[2 + r][1], X[1][c], fma(-S[2 + r][0], X[0][c], S[2 + r][2 + c]));
+    // adjugate of the 3x3 block
+    const double c00 = fma(T[1][1], T[2][2], -T[1][2] * T[2][1]);
+    const double c01 = fma(T[1][2], T[2][0], -T[1][0] * T[2][2]);
+    const double c02 = fma(T[1][0], T[2][1], -T[1][1] * T[2][0]);
+    const double c10 = fma(T[0][2], T[2][1], -T[0][1] * T[2][2]);
+    const double c11 = fma(T[0][0], T[2][2], -T[0][2] * T[2][0]);
+    const double c12 = fma(T[0][1], T[2][0], -T[0][0] * T[2][1]);
+    const double c20 = fma(T[0][1], T[1][2], -T[0][2] * T[1][1]);
+    const double c21 = fma(T[0][2], T[1][0], -T[0][0] * T[1][2]);
+    const double c22 = fma(T[0][0], T[1][1], -T[0][1] * T[1][0]);
+    const double det3 = fma(T[0][0], c00, fma(T[0][1], c01, T[0][2] * c02));
+    const double r3 = 1.0 / det3;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const double b0 = T[0][3 + q], b1 = T[1][3 + q], b2 = T[2][3 + q];
+        const double z2 = fma(c00, b0, fma(c10, b1, c20 * b2)) * r3;
+        const double z3 = fma(c01, b0, fma(c11, b1, c21 * b2)) * r3;
+        const double z4 = fma(c02, b0, fma(c12, b1, c22 * b2)) * r3;
+        S[2][5 + q] = z2;
+        S[3][5 + q] = z3;
+        S[4][5 + q] = z4;
+        S[0][5 + q] = fma(-X[0][2], z4, fma(-X[0][1], z3, fma(-X[0][0], z2, X[0][3 + q])));
+        S[1][5 + q] = fma(-X[1][2], z4, fma(-X[1][1], z3, fma(-X[1][0], z2, X[1][3 + q])));
+    }
+    return fmin(fabs(detP), fabs(det3));
+}
+
 // Partial (row) pivoting variant for the rare ill-scaled case.  M is the untouched copy of the system.
 #if defined(__CUDACC__)
 __host__ __device__ __noinline__
@@ -279,8 +337,8 @@ static void solve5x2_pivoted(const double* M /*[35]*/, double* X /*[10]: x0[5], 
 
 // Quasi-Newton direction delta = solve(K, -Q) with K the reference's approximate Jacobian (S5:129-289)
 // evaluated at the point of `e`, computed through the block structure described at the top.
-template <bool ALPHA, int HILL>
-HMX_HD void direction(const SolverConsts& K, const Eval& e, const double (&A)[15], const double (&b)[5],
+template <bool ALPHA, int HILL, class AT>
+HMX_HD void direction(const SolverConsts& K, const Eval& e, const AT& A, const double (&b)[5],
                       double (&delta)[12]) {
     double a0[5], a1[5], b0[5], b1[5], d0[5], d1[5];  // D_i^{-1} r_i, D_i^{-1} u_i, D_i^{-1} [psi;phi]
     double S[5][7];
@@ -341,7 +399,12 @@ HMX_HD void direction(const SolverConsts& K, const Eval& e, const double (&A)[15
         }
     };
     build_S(S);
-    if (!(solve5x2_natural(S) >= kPivotFloor)) {  // rare: rebuild and redo with row pivoting
+#if defined(HMX_SOLVE_NATURAL)
+    const double health = solve5x2_natural(S);
+#else
+    const double health = solve5x2_block23(S);
+#endif
+    if (!(health >= kPivotFloor)) {  // rare: rebuild and redo with row pivoting
         double T[5][7], X[10];
         build_S(T);
         solve5x2_pivoted(&T[0][0], X);
