@@ -77,6 +77,14 @@ def main():
         phi_init=np.full(5, 0.02), bounds=conds["Dysbiotic_HOBIC"]["bounds"], locked=[], days=[1, 3, 6, 10, 15, 21],
     )
     legacy["sigma_obs"] = np.full((legacy["data"].shape[0], 5), legacy["sigma_scalar"])
+    # The stored run predates the current model_config/prior_bounds.json (its samples reach 30 in a23/a35 and
+    # 20 in a45); the run directory does not record its bounds, so they are inferred from the extent of its
+    # 2000 posterior samples, snapped outward to the grid of bound values the reference uses.
+    grid = np.array([-3.0, -1.0, -0.5, 0.0, 0.5, 1.0, 2.5, 3.0, 5.0, 10.0, 15.0, 20.0, 30.0])
+    s_leg = np.load(legacy_dir / "samples.npy")
+    legacy["bounds"] = [(float(grid[grid <= lo + 1e-9].max()), float(grid[grid >= hi - 1e-9].min()))
+                        for lo, hi in zip(s_leg.min(0), s_leg.max(0))]
+    legacy["bounds_note"] = "inferred from the sample extent of _runs/Dysbiotic_HOBIC_K0.05_n4.0_1k30/samples.npy"
     conds["Dysbiotic_HOBIC_legacy_1k30"] = legacy
 
     def ser(d):
