@@ -23,7 +23,7 @@ static void run_lane(const SolverConsts& K, const CondConsts& C, const ThetaMap&
     while (!done) {
         if (lane_trip<ALPHA, HILL>(K, s)) {
             double old[11];
-            memcpy(old, s.gp, sizeof(old));
+            for (int i = 0; i < 11; ++i) old[i] = s.gp[i];
             done = lane_advance(K, s);
             if (g_arr) memcpy(g_arr + (size_t)s.step_idx * 12, s.g, 12 * sizeof(double));
             for (int o = 0; o < C.n_obs; ++o) {

@@ -77,6 +77,13 @@ __global__ void __launch_bounds__(kOdeThreads, kOdeMinBlocks) ode_kernel(const _
         static_assert(HMX_A_IN_SMEM == kOdeThreads, "HMX_A_IN_SMEM must equal the ODE block size");
         s.A.p = smA + threadIdx.x;
 #endif
+#if defined(HMX_STATE_IN_SMEM)
+        __shared__ double smGP[11 * kOdeThreads];
+        __shared__ double smD[12 * kOdeThreads];
+        static_assert(HMX_STATE_IN_SMEM == kOdeThreads, "HMX_STATE_IN_SMEM must equal the ODE block size");
+        s.gp.p = smGP + threadIdx.x;
+        s.d.p = smD + threadIdx.x;
+#endif
         {
             double th[HMX_NTHETA];
             const double* tp = P.theta + w * HMX_NTHETA;

@@ -39,10 +39,26 @@ struct LaneA {
 };
 #endif
 
+#if defined(HMX_STATE_IN_SMEM) && defined(__CUDACC__)
+// previous time level and Newton direction parked in shared memory too: 23 more doubles out of the register
+// file, which is what lets a third warp per scheduler become resident (168 registers / thread)
+using LaneGP = SmemCol<HMX_STATE_IN_SMEM>;
+using LaneD = SmemCol<HMX_STATE_IN_SMEM>;
+#else
+template <int N>
+struct RegArr {
+    double v[N];
+    HMX_HD double& operator[](int k) { return v[k]; }
+    HMX_HD const double& operator[](int k) const { return v[k]; }
+};
+using LaneGP = RegArr<11>;
+using LaneD = RegArr<12>;
+#endif
+
 struct Lane {
-    double gp[11];   // previous time level: phi(5), phi_0, psi(5)
+    LaneGP gp;       // previous time level: phi(5), phi_0, psi(5)
     double g[12];    // current Newton iterate
-    double d[12];    // current Newton direction
+    LaneD d;         // current Newton direction
     LaneA A;         // packed symmetric interaction matrix
     double b[5];     // decay vector (only read when alpha != 0)
     double normQ;    // ||Q||_inf at the iterate
