@@ -63,76 +63,87 @@ struct OdeParams {
     int n_cond;
 };
 
+// ONE flat loop per lane.  Every pass is one state-machine trip; fetching the next particle, the per-step
+// bookkeeping and the final stores are (rare) predicated blocks INSIDE that loop.  With a nested
+// "for each particle { while (!done) trip }" the lanes of a warp that finish a particle early wait at the
+// inner loop's reconvergence point for the slowest lane (SIMT), which measured as 18.5 of 32 active threads
+// per instruction; the flat loop keeps all lanes of a warp in the same trip until the work list is empty.
 template <bool ALPHA, int HILL>
 __global__ void __launch_bounds__(kOdeThreads, kOdeMinBlocks) ode_kernel(const __grid_constant__ OdeParams P) {
     const long long nthreads = (long long)gridDim.x * blockDim.x;
     long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    while (pos < P.N) {
-        const long long w = P.order ? (long long)P.order[pos] : pos;
-        const int c = cond_index(P.cond_id, w, P.n_cond);
-        const OdeCond& oc = P.cond[c];
-        Lane s;
+    Lane s;
 #if defined(HMX_A_IN_SMEM)
-        __shared__ double smA[15 * kOdeThreads];
-        static_assert(HMX_A_IN_SMEM == kOdeThreads, "HMX_A_IN_SMEM must equal the ODE block size");
-        s.A.p = smA + threadIdx.x;
+    __shared__ double smA[15 * kOdeThreads];
+    static_assert(HMX_A_IN_SMEM == kOdeThreads, "HMX_A_IN_SMEM must equal the ODE block size");
+    s.A.p = smA + threadIdx.x;
 #endif
 #if defined(HMX_STATE_IN_SMEM)
-        __shared__ double smGP[11 * kOdeThreads];
-        __shared__ double smD[12 * kOdeThreads];
-        static_assert(HMX_STATE_IN_SMEM == kOdeThreads, "HMX_STATE_IN_SMEM must equal the ODE block size");
-        s.gp.p = smGP + threadIdx.x;
-        s.d.p = smD + threadIdx.x;
+    __shared__ double smGP[11 * kOdeThreads];
+    __shared__ double smD[12 * kOdeThreads];
+    static_assert(HMX_STATE_IN_SMEM == kOdeThreads, "HMX_STATE_IN_SMEM must equal the ODE block size");
+    s.gp.p = smGP + threadIdx.x;
+    s.d.p = smD + threadIdx.x;
 #endif
-        {
+    long long w = 0;       // evaluation this lane is working on
+    int c = 0;             // its condition
+    int next_obs = 0, next_t = 0x7fffffff;
+    bool have = false;     // lane holds an unfinished evaluation
+
+    for (;;) {
+        if (!have) {
+            if (pos >= P.N) break;  // work list empty: this lane is finished for good
+            w = P.order ? (long long)P.order[pos] : pos;
+            c = cond_index(P.cond_id, w, P.n_cond);
             double th[HMX_NTHETA];
             const double* tp = P.theta + w * HMX_NTHETA;
 #pragma unroll
             for (int k = 0; k < HMX_NTHETA; ++k) th[k] = __ldg(tp + k);
-            lane_init(P.K, s, th, oc.g0);
+            lane_init(P.K, s, th, P.cond[c].g0);
+            if (P.traj) {
+                double* tr = P.traj + w * (long long)(P.K.n_steps + 1) * 12;
+#pragma unroll
+                for (int i = 0; i < 12; ++i) tr[i] = s.g[i];
+            }
+            next_obs = 0;
+            next_t = (P.cond[c].n_obs > 0) ? max(P.cond[c].idx[0], 1) : 0x7fffffff;
+            have = true;
         }
-        double* tr = P.traj ? P.traj + w * (long long)(P.K.n_steps + 1) * 12 : nullptr;
-        if (tr) {
-#pragma unroll
-            for (int i = 0; i < 12; ++i) tr[i] = s.g[i];
-        }
-        int next_obs = 0;
-        const int n_obs = oc.n_obs;
-        int next_t = (n_obs > 0) ? max(oc.idx[0], 1) : 0x7fffffff;
-        double* pr = P.pairs + w * P.pair_stride;
-
-        bool done = false;
-        while (!done) {
-            if (lane_trip<ALPHA, HILL>(P.K, s)) {
-                if (s.step_idx + 1 == next_t) {
-                    // observation row reached: keep (g_t, g_{t-1}) for the sensitivity kernel
-                    do {
-                        double* q = pr + next_obs * kPairStride;
-#pragma unroll
-                        for (int i = 0; i < 12; ++i) q[i] = s.g[i];
-#pragma unroll
-                        for (int i = 0; i < 11; ++i) q[12 + i] = s.gp[i];
-                        q[23] = 0.0;
-                        ++next_obs;
-                        next_t = (next_obs < n_obs) ? max(oc.idx[next_obs], 1) : 0x7fffffff;
-                    } while (s.step_idx + 1 == next_t);
-                }
-                done = lane_advance(P.K, s);
-                if (tr) {
-                    double* q = tr + (long long)s.step_idx * 12;
+        if (lane_trip<ALPHA, HILL>(P.K, s)) {
+            // end of a time step: s.g = g_arr[step_idx + 1], s.gp = g_arr[step_idx]
+            if (s.step_idx + 1 == next_t) {
+                // observation row reached: keep (g_t, g_{t-1}) for the sensitivity kernel
+                const OdeCond& oc = P.cond[c];
+                double* pr = P.pairs + w * P.pair_stride;
+                do {
+                    double* q = pr + next_obs * kPairStride;
 #pragma unroll
                     for (int i = 0; i < 12; ++i) q[i] = s.g[i];
-                }
+#pragma unroll
+                    for (int i = 0; i < 11; ++i) q[12 + i] = s.gp[i];
+                    q[23] = 0.0;
+                    ++next_obs;
+                    next_t = (next_obs < oc.n_obs) ? max(oc.idx[next_obs], 1) : 0x7fffffff;
+                } while (s.step_idx + 1 == next_t);
+            }
+            const bool done = lane_advance(P.K, s);
+            if (P.traj) {
+                double* q = P.traj + w * (long long)(P.K.n_steps + 1) * 12 + (long long)s.step_idx * 12;
+#pragma unroll
+                for (int i = 0; i < 12; ++i) q[i] = s.g[i];
+            }
+            if (done) {
+                P.status[w] = s.status;
+                P.iters[w] = s.iters;
+                P.trips[w] = s.trips;
+                atomicAdd(P.totals + 0, (unsigned long long)s.iters);
+                atomicAdd(P.totals + 1, (unsigned long long)s.trips);
+                atomicAdd(P.cond_trips + c, (unsigned long long)s.trips);
+                atomicAdd(P.cond_evals + c, 1ULL);
+                pos = (long long)atomicAdd(P.work_counter, 1ULL) + nthreads;
+                have = false;
             }
         }
-        P.status[w] = s.status;
-        P.iters[w] = s.iters;
-        P.trips[w] = s.trips;
-        atomicAdd(P.totals + 0, (unsigned long long)s.iters);
-        atomicAdd(P.totals + 1, (unsigned long long)s.trips);
-        atomicAdd(P.cond_trips + c, (unsigned long long)s.trips);
-        atomicAdd(P.cond_evals + c, 1ULL);
-        pos = (long long)atomicAdd(P.work_counter, 1ULL) + nthreads;
     }
 }
 
