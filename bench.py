@@ -6,7 +6,7 @@
         bench.py --gpus N --steps K --warmup W
 
 Workload (config.workload): BASELINE.json configs[4], the synthetic likelihood throughput sweep -- per GPU
-4 conditions x 65,536 theta ~ U(prior bounds of the condition) (np.random.default_rng(20260101 + c + 97 rank)),
+4 conditions x 262,144 theta ~ U(prior bounds of the condition) (np.random.default_rng(20260101 + c + 97 rank)),
 production solver settings (dt=1e-4, 2500 steps, c=25, alpha=0, Kp1=1e-4, K_hill=0.05, n_hill=4), TSM
 variance on.  One evaluation = one (theta, condition) pair = one 2500-step implicit solve + its Gaussian
 log-likelihood.  Weak scaling: the per-GPU batch is fixed, ranks hold disjoint particles.
@@ -41,17 +41,18 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-N_PER_COND = 65536
+N_PER_COND = 262144
 N_COND = 4
 METRIC = "particle_ode_likelihood_evals_per_sec"
 UNIT = "evals/s"
 
 # Executed FP64 flops (DFMA = 2, DMUL = DADD = 1) of the ODE kernel per residual evaluation ("trip") and per
-# quasi-Newton direction solve, calibrated from the ncu capture profiles/r01a_ode_kernel_first.json
-# (thread-level sass op counters / the kernel's own trip and iteration counters; split by the static SASS
-# ratio of residual() : direction()).  DESIGN.md section "Roofline accounting" has the derivation.
-FLOPS_PER_RESIDUAL = 376.0
-FLOPS_PER_DIRECTION = 1093.0
+# quasi-Newton direction solve, calibrated from the ncu capture profiles/r01b_ode_kernel_large_batch.json
+# (thread-level sass op counters: 1.8806e12 DFMA + 1.2143e12 DMUL + 3.584e11 DADD thread-instructions for the
+# kernel's own counters of 4.5913e9 residual evaluations and 3.4175e9 directions; split between the two by the
+# static SASS ratio of residual() : direction() = 443 : 1287).  DESIGN.md "Roofline accounting" has the derivation.
+FLOPS_PER_RESIDUAL = 367.0
+FLOPS_PER_DIRECTION = 1067.0
 # the reference-equivalent count of SURVEY.md section 8(d): dense Q + K + dgesv per iteration, Q per extra trial
 REF_FLOPS_PER_ITER = 2778.0
 REF_FLOPS_PER_TRIAL = 384.0
@@ -114,7 +115,7 @@ def synth_batch(rank: int):
     return wl
 
 
-def cpu_baseline(wl, budget_s: float = 12.0, max_evals: int = 8192) -> dict:
+def cpu_baseline(wl, budget_s: float = 12.0, max_evals: int = 16384) -> dict:
     """The oracle port on all host threads, on a bounded prefix-sample of the same workload (equal share per condition)."""
     from oracle import oracle as orc
 
@@ -177,7 +178,7 @@ def workload_config(n_gpus: int, per_step_note: str = "") -> dict:
                     f"{N_PER_COND} theta ~ U(prior bounds) per GPU, Hamilton 5-species ODE dt=1e-4 x 2500 steps, K_hill=0.05 n_hill=4, TSM variance on",
         "evals_per_gpu_per_step": N_PER_COND * N_COND, "global_evals_per_step": N_PER_COND * N_COND * n_gpus,
         "n_steps_ode": 2500, "parallelism": f"particles sharded over {n_gpus} GPU(s), logL all-gather + covariance all-reduce per step",
-        "l2_policy": "inputs+scratch per step (42 MB theta + 252 MB observation pairs per GPU) exceed the 126 MB L2; no flush needed",
+        "l2_policy": "inputs+scratch per step (168 MB theta + 1 GB observation pairs per GPU) exceed the 126 MB L2; no flush needed",
         "note": per_step_note,
     }
 
