@@ -243,6 +243,18 @@ def main():
         logL_max=l_ref.max(), logL_min=l_ref.min(), MAP=s_ref[np.argmax(l_ref)],
         chain_means=np.stack([s_ref[:1000].mean(0), s_ref[1000:].mean(0)]),
     )
+    # the reference's own credible intervals for those samples (written by its run-directory code, MAIN:378-456)
+    import csv as _csv
+
+    with open(legacy_dir / "parameter_summary.csv") as fh:
+        rows = list(_csv.DictReader(fh))
+    np.savez_compressed(
+        OUT / "posterior_dh_1k30_samples.npz", samples=s_ref.astype(np.float64),
+        hdi_lower=np.array([float(r["hdi_lower"]) for r in rows]), hdi_upper=np.array([float(r["hdi_upper"]) for r in rows]),
+        et_lower=np.array([float(r["et_lower"]) for r in rows]), et_upper=np.array([float(r["et_upper"]) for r in rows]),
+        median=np.array([float(r["median"]) for r in rows]), mean=np.array([float(r["mean"]) for r in rows]),
+        credibility=float(legacy_cfg.get("hdi_credibility", 0.95)),
+    )
     manifest["production_run"] = {"samples": list(s_ref.shape), "logL_max": float(l_ref.max()), "elapsed_s": 226864.8}
 
     manifest["wall_s"] = round(time.time() - t_start, 1)

@@ -68,8 +68,13 @@ struct OdeParams {
 // "for each particle { while (!done) trip }" the lanes of a warp that finish a particle early wait at the
 // inner loop's reconvergence point for the slowest lane (SIMT), which measured as 18.5 of 32 active threads
 // per instruction; the flat loop keeps all lanes of a warp in the same trip until the work list is empty.
+#if defined(HMX_ODE_MAXNREG)
+#define HMX_ODE_BOUNDS __maxnreg__(HMX_ODE_MAXNREG)
+#else
+#define HMX_ODE_BOUNDS __launch_bounds__(kOdeThreads, kOdeMinBlocks)
+#endif
 template <bool ALPHA, int HILL>
-__global__ void __launch_bounds__(kOdeThreads, kOdeMinBlocks) ode_kernel(const __grid_constant__ OdeParams P) {
+__global__ void HMX_ODE_BOUNDS ode_kernel(const __grid_constant__ OdeParams P) {
     const long long nthreads = (long long)gridDim.x * blockDim.x;
     long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     Lane s;

@@ -40,6 +40,24 @@ def build_species_sigma(sigma_global: float, n_species: int = 5, vd_species_idx:
     return s
 
 
+def build_replicate_sigma(replicate_csv: str, condition: str, cultivation: str, days: list, species_map: dict,
+                          n_species: int = 5, min_sigma: float = 0.005) -> np.ndarray:
+    """Per-(day, species) sigma = IQR / 1.35 of the replicate percentages, floored at min_sigma, in fraction
+    space (EV:134-187).  Setup-time host work; needs the reference's fig3_species_distribution_replicates.csv."""
+    import pandas as pd
+
+    df = pd.read_csv(replicate_csv)
+    dc = df[(df["condition"] == condition) & (df["cultivation"] == cultivation)]
+    sigma = np.full((len(days), n_species), min_sigma, dtype=np.float64)
+    for i, day in enumerate(days):
+        for name, idx in species_map.items():
+            vals = dc[(dc["species"] == name) & (dc["day"] == day)]["distribution_pct"].values
+            if len(vals) >= 3:
+                iqr = np.percentile(vals, 75) - np.percentile(vals, 25)
+                sigma[i, idx] = max(iqr / 1.35, min_sigma * 100.0) / 100.0
+    return sigma
+
+
 def build_likelihood_weights(n_obs: int, n_species: int, pg_species_idx: int = 4, n_late: int = 2,
                              lambda_pg: float = 5.0, lambda_late: float = 3.0) -> np.ndarray:
     """Weight matrix: column pg_species_idx x lambda_pg, last n_late rows x lambda_late (EV:190-234)."""
