@@ -76,8 +76,30 @@ def compare_with_reference(samples, ll):
             "reference_elapsed_s": 226864.8}
 
 
+def run_merged(keys, n_particles, n_chains, seed=42, n_mutation_steps=5, n_stages=30):
+    """All conditions x chains concurrently, likelihood launches merged (tmcmc202601_b200.batch)."""
+    from tmcmc202601_b200 import batch
+
+    conds = workloads.load_conditions()
+    jobs = []
+    for key in keys:
+        cd = conds[key]
+        base = np.full(20, 1.5)
+        base[cd["locked"]] = 0.0
+        jobs.append(dict(model_tag=f"{cd['condition']}_{cd['cultivation']}", data=cd["data"], idx_sparse=cd["idx_sparse"],
+                         sigma_obs=cd["sigma_obs"], phi_init=cd["phi_init"], prior_bounds=cd["bounds"], theta_base=base,
+                         active_indices=cd["active_indices"]))
+    out, stats = batch.run_batch_TMCMC(jobs, workloads.PRODUCTION_SOLVER, n_particles=n_particles, n_stages=n_stages,
+                                       n_chains=n_chains, seed=seed, n_mutation_steps=n_mutation_steps)
+    summary = {"mode": "merged", "conditions": list(keys), "n_particles": n_particles, "n_chains": n_chains, **stats,
+               "per_condition": [{"condition": k, "converged": o["converged"], "stages": [len(r.stage_summary) for r in o["results"]],
+                                  "logL_max": float(max(l.max() for l in o["logL"]))} for k, o in zip(keys, out)]}
+    return summary, out
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--merged", action="store_true", help="run the four current-default conditions concurrently")
     ap.add_argument("--particles", type=int, default=1000)
     ap.add_argument("--chains", type=int, default=2)
     ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "tmcmc_runs.json"))
@@ -87,6 +109,11 @@ def main():
     if args.only:
         keys = [k for k in keys if k in args.only.split(",")]
     results = []
+    if args.merged:
+        summary, _ = run_merged(workloads.CONDITION_KEYS, args.particles, args.chains)
+        print(json.dumps(summary), flush=True)
+        results.append(summary)
+        keys = []
     for k in keys:
         out, samples, ll = run_condition(k, args.particles, args.chains)
         if k.endswith("legacy_1k30") and args.particles >= 500:

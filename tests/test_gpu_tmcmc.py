@@ -67,3 +67,20 @@ def test_production_run_posterior_matches_reference_run(built):
     assert cmp_["quantile_shift_over_std_max"] < 0.5
     assert abs(out["logL_max"] - cmp_["logL_max_ref"]) < 1.5 and abs(out["logL_mean"] - cmp_["logL_mean_ref"]) < 0.5
     assert out["wall_s"] < 120.0
+
+
+def test_merged_four_condition_run_equals_sequential(built):
+    """BASELINE.json configs[2]: the four conditions x 2 chains run concurrently with merged launches; every
+    chain must equal the chain run on its own (bitwise), and the whole batch must finish in seconds."""
+    import sys
+
+    sys.path.insert(0, str(GOLDEN.parents[1] / "scripts"))
+    import run_production_tmcmc as rp
+
+    summary, out = rp.run_merged(workloads.CONDITION_KEYS, 200, 2)
+    assert all(all(o["converged"]) for o in out) and summary["merged_launches"] < 40
+    solo, samples, ll = rp.run_condition("Commensal_HOBIC", 200, 2)
+    k = workloads.CONDITION_KEYS.index("Commensal_HOBIC")
+    assert np.array_equal(np.concatenate(out[k]["chains"], axis=0), samples)
+    assert np.array_equal(np.concatenate(out[k]["logL"]), ll)
+    print(summary)
