@@ -192,3 +192,26 @@ def test_large_batch_is_order_independent(engines):
     big = eng.loglik_batch(wl.theta[pick], wl.cond_id[pick])
     assert np.array_equal(big, base[pick])
     assert np.isfinite(big).all() and (big > -1e19).all()
+
+
+def test_multi_chunk_batches_equal_single_chunk(engines, monkeypatch):
+    """Batches above the chunk size (4 Mi evaluations by default) are processed in pieces with staging-buffer
+    reuse; HMX_CHUNK_EVALS shrinks the chunk so the path is exercised at test size."""
+    from tmcmc202601_b200.engine import HamiltonEngine
+
+    wl = workloads.four_condition_workload(50, seed=21, interleave=True)
+    ref = engines(wl.config).loglik_batch(wl.theta, wl.cond_id, return_status=True, return_obs=True)
+    monkeypatch.setenv("HMX_CHUNK_EVALS", "37")
+    eng = HamiltonEngine(wl.config, device=0)
+    try:
+        got = eng.loglik_batch(wl.theta, wl.cond_id, return_status=True, return_obs=True)
+        for a, b in zip(got, ref):
+            assert np.array_equal(a, b)
+        c = eng.counters()
+        assert c["newton_iters"] == int(ref[2].astype(np.int64).sum())  # counters accumulate over the chunks
+        g1, _, _ = eng.trajectory_batch(wl.theta[:80], wl.cond_id[:80])
+    finally:
+        eng.close()
+    monkeypatch.delenv("HMX_CHUNK_EVALS")
+    g0, _, _ = engines(wl.config).trajectory_batch(wl.theta[:80], wl.cond_id[:80])
+    assert np.array_equal(g0, g1)

@@ -25,7 +25,7 @@ using namespace hmx;
 
 namespace {
 
-constexpr long long kChunkEvals = 1ll << 22;
+constexpr long long kDefaultChunkEvals = 1ll << 22;
 
 struct DevBuf {
     void* p = nullptr;
@@ -66,6 +66,7 @@ struct hmx_ctx {
     bool timing_pending = false;
     double last_ode_ms = 0.0;
     long long last_evals = 0;
+    long long chunk_evals = kDefaultChunkEvals;  // HMX_CHUNK_EVALS overrides (tests exercise the multi-chunk path with it)
     long long launches = 0;
 };
 
@@ -285,8 +286,8 @@ int batch_impl(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, long l
     const long long obs_stride = (long long)std::max(ctx->n_obs_max, 1) * 12;
     const long long traj_stride = (long long)(ctx->cfg.n_steps + 1) * 12;
     bool need_sync = false;
-    for (long long off = 0; off < N; off += kChunkEvals) {
-        const long long n = std::min(kChunkEvals, N - off);
+    for (long long off = 0; off < N; off += ctx->chunk_evals) {
+        const long long n = std::min(ctx->chunk_evals, N - off);
         int rc;
         const void *d_theta, *d_cond;
         void *d_logL, *d_obs, *d_status, *d_iters, *d_traj;
@@ -311,7 +312,7 @@ int batch_impl(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, long l
         const bool any_host = h_logL || h_obs || h_status || h_iters || h_traj;
         need_sync = need_sync || any_host;
         // staging buffers are reused by the next chunk: drain before overwriting them
-        if (off + kChunkEvals < N && (any_host || !is_device_ptr(theta))) CU(cudaStreamSynchronize(ctx->stream));
+        if (off + ctx->chunk_evals < N && (any_host || !is_device_ptr(theta))) CU(cudaStreamSynchronize(ctx->stream));
     }
     if (need_sync) CU(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -386,6 +387,10 @@ int hmx_create(hmx_ctx** out, const hmx_config* cfg, int32_t device) {
     CU_CREATE(cudaEventCreate(&ctx->ev0));
     CU_CREATE(cudaEventCreate(&ctx->ev1));
     ctx->ode_blocks_per_sm = query_occupancy(ctx);
+    if (const char* ce = getenv("HMX_CHUNK_EVALS")) {
+        const long long v = atoll(ce);
+        if (v > 0) ctx->chunk_evals = v;
+    }
     *out = ctx;
     return HMX_OK;
 }

@@ -55,11 +55,18 @@ using LaneGP = RegArr<11>;
 using LaneD = RegArr<12>;
 #endif
 
+#if defined(HMX_STASH_IN_SMEM) && defined(__CUDACC__)
+using LaneStash = SmemCol<HMX_STASH_IN_SMEM>;  // direction-solve scratch (30 doubles) parked in shared memory
+#else
+using LaneStash = RegStash;
+#endif
+
 struct Lane {
     LaneGP gp;       // previous time level: phi(5), phi_0, psi(5)
     double g[12];    // current Newton iterate
     LaneD d;         // current Newton direction
     LaneA A;         // packed symmetric interaction matrix
+    LaneStash stash; // scratch of the direction solve
     double b[5];     // decay vector (only read when alpha != 0)
     double normQ;    // ||Q||_inf at the iterate
     double step;     // current line-search step length
@@ -160,7 +167,7 @@ HMX_HD bool lane_trip(const SolverConsts& K, Lane& s) {
         s.g[11] = x[11];
     }
     if (need_dir) {
-        direction<ALPHA, HILL>(K, e, s.A, s.b, s.d);
+        direction<ALPHA, HILL>(K, e, s.A, s.b, s.d, s.stash);
         double chk = 0.0;
 #pragma unroll
         for (int i = 0; i < 12; ++i) chk = fma(s.d[i], 0.0, chk);

@@ -117,16 +117,17 @@ HMX_HD void hill_powers(const SolverConsts& K, double x, double& xn, double& xn1
     }
 }
 
-// Everything one residual evaluation produces that the direction solve reuses.
+// Everything one residual evaluation produces that the direction solve reuses.  Kept small on purpose: the
+// kernel is register-bound, so the barrier derivatives are finished inside the residual (while 1/(v(v-1)) is
+// still at hand) instead of carrying the reciprocals across the accept/reject decision.
 struct Eval {
-    double ph[5], ps[5], ph0;      // clipped values the residual was evaluated at
-    double rph[5], rps[5];         // 1/(v(v-1))
-    double fph[5], fps[5];         // barrier value  -2Kp1(2v-1) r^3
-    double f0, r0;                 // same for phi_0
+    double ph[5], ps[5];           // clipped values the residual was evaluated at
     double p[5];                   // phi_i psi_i
     double I[5];                   // gated interaction (A p)_i * h_i
-    double Iraw4, h, dh_dx;        // Hill gate state (h = 1 when the gate is off)
     double phd[5], psd[5];         // time derivatives
+    double phip[5], psip[5];       // barrier derivatives phi_p, psi_p of S5:185-189
+    double K55;                    // phi0_p + 1/dt  (S5:191-194, 222)
+    double Iraw4, h, dh_dx;        // Hill gate state (h = 1 when the gate is off)
     double Q[12];
     double norm;                   // ||Q||_inf
     bool nan;                      // any(isnan(Q))
@@ -142,24 +143,31 @@ HMX_HD void residual(const SolverConsts& K, const double (&x)[12], const GPT& gp
         e.ph[i] = clip01(x[i]);
         e.ps[i] = clip01(x[6 + i]);
     }
-    e.ph0 = clip01(x[5]);
+    const double ph0 = clip01(x[5]);
     const double m2K = -2.0 * K.Kp1;
+    double fph[5], fps[5];  // barrier values -2Kp1(2v-1) r^3
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
         const double v = e.ph[i], u = e.ps[i];
-        const double rv = 1.0 / fma(v, v, -v), ru = 1.0 / fma(u, u, -u);
-        e.rph[i] = rv;
-        e.rps[i] = ru;
-        e.fph[i] = (m2K * fma(2.0, v, -1.0)) * (rv * rv * rv);
-        e.fps[i] = (m2K * fma(2.0, u, -1.0)) * (ru * ru * ru);
+        const double wv = fma(v, v, -v), wu = fma(u, u, -u);
+        const double rv = 1.0 / wv, ru = 1.0 / wu;
+        const double sv = fma(2.0, v, -1.0), su = fma(2.0, u, -1.0);
+        fph[i] = (m2K * sv) * (rv * rv * rv);
+        fps[i] = (m2K * su) * (ru * ru * ru);
+        e.phip[i] = -fph[i] * fma(3.0 * sv, rv, 2.0);                        // S5:185-187
+        const double ru2 = ru * ru;
+        e.psip[i] = (4.0 * K.Kp1) * fma(5.0, wu, 3.0) * (ru2 * ru2);          // S5:189
         e.p[i] = v * u;
         e.phd[i] = (v - gp[i]) * K.inv_dt;
         e.psd[i] = (u - gp[6 + i]) * K.inv_dt;
     }
+    double f0;
     {
-        const double v = e.ph0;
-        e.r0 = 1.0 / fma(v, v, -v);
-        e.f0 = (m2K * fma(2.0, v, -1.0)) * (e.r0 * e.r0 * e.r0);
+        const double v = ph0;
+        const double r0 = 1.0 / fma(v, v, -v);
+        const double s0 = fma(2.0, v, -1.0);
+        f0 = (m2K * s0) * (r0 * r0 * r0);
+        e.K55 = -f0 * fma(3.0 * s0, r0, 2.0) + K.inv_dt;                      // S5:191-194, 222
     }
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
@@ -191,17 +199,17 @@ HMX_HD void residual(const SolverConsts& K, const double (&x)[12], const GPT& gp
         // Q_i, S5:98-106
         // (1/eta)[gamma + (eta_phi + eta psi^2) phidot + eta phi psi psidot], with 1/eta distributed
         const double t2 = fma(K.inv_eta[i], gam, fma(fma(u, u, K.etaphi_eta[i]), e.phd[i], e.p[i] * e.psd[i]));
-        const double qi = e.fph[i] + t2 - K.c_eta[i] * u * e.I[i];
+        const double qi = fph[i] + t2 - K.c_eta[i] * u * e.I[i];
         // Q_{6+i}, S5:116-123
-        double qs = e.fps[i] + fma(e.p[i], e.phd[i], v * v * e.psd[i]) - K.c_eta[i] * v * e.I[i];
+        double qs = fps[i] + fma(e.p[i], e.phd[i], v * v * e.psd[i]) - K.c_eta[i] * v * e.I[i];
         if (ALPHA) qs += (b[i] * K.alpha_eta[i]) * u;
         e.Q[i] = qi;
         e.Q[6 + i] = qs;
         nrm = fmax(nrm, fmax(fabs(qi), fabs(qs)));
         asum += fabs(qi) + fabs(qs);
     }
-    e.Q[5] = gam + e.f0 + (e.ph0 - gp[5]) * K.inv_dt;                              // S5:109-113
-    e.Q[11] = ((((e.ph[0] + e.ph[1]) + e.ph[2]) + e.ph[3]) + e.ph[4]) + e.ph0 - 1.0;  // S5:126
+    e.Q[5] = gam + f0 + (ph0 - gp[5]) * K.inv_dt;                                  // S5:109-113
+    e.Q[11] = ((((e.ph[0] + e.ph[1]) + e.ph[2]) + e.ph[3]) + e.ph[4]) + ph0 - 1.0;    // S5:126
     nrm = fmax(nrm, fmax(fabs(e.Q[5]), fabs(e.Q[11])));
     asum += fabs(e.Q[5]) + fabs(e.Q[11]);
     e.norm = nrm;
@@ -335,78 +343,84 @@ static void solve5x2_pivoted(const double* M /*[35]*/, double* X /*[10]: x0[5], 
     }
 }
 
+// Scratch for the per-species vectors D_i^{-1} r_i, D_i^{-1} u_i, D_i^{-1} [psi_i; phi_i] (30 doubles) that are
+// produced before and consumed after the 5x5 solve.  In the kernel they are parked in shared memory so they
+// do not occupy registers during the elimination; on the host / in the observation kernel a plain array.
+struct RegStash {
+    double v[30];
+    HMX_HD double& operator[](int k) { return v[k]; }
+};
+
 // Quasi-Newton direction delta = solve(K, -Q) with K the reference's approximate Jacobian (S5:129-289)
 // evaluated at the point of `e`, computed through the block structure described at the top.
-template <bool ALPHA, int HILL, class AT, class DT>
-HMX_HD void direction(const SolverConsts& K, const Eval& e, const AT& A, const double (&b)[5],
-                      DT& delta) {
-    double a0[5], a1[5], b0[5], b1[5], d0[5], d1[5];  // D_i^{-1} r_i, D_i^{-1} u_i, D_i^{-1} [psi;phi]
+template <bool ALPHA, int HILL, class AT, class DT, class ST>
+HMX_HD void direction(const SolverConsts& K, const Eval& e, const AT& A, const double (&b)[5], DT& delta, ST& stash) {
     double S[5][7];
-    double hrow[5];
+    double srow[5];  // -c/eta_i h_i: row scaling of the A-derived coefficients C_ij = srow_i A_ij
 #pragma unroll
-    for (int i = 0; i < 5; ++i) hrow[i] = 1.0;
-    if (HILL != 0) hrow[4] = e.h;  // h == 1 reproduces "no correction" (S5:250)
+    for (int i = 0; i < 5; ++i) srow[i] = -K.c_eta[i];
+    if (HILL != 0) srow[4] *= e.h;  // h == 1 reproduces "no correction" (S5:250)
+    // the dh/dx outer product at block (4,3), S5:273-287
+    double c43x = 0.0;
+    if (HILL != 0) {
+        if (e.h < 1.0) c43x = -K.c_eta[4] * e.Iraw4 * e.dh_dx;
+    }
 
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
         const double v = e.ph[i], u = e.ps[i], pd = e.phd[i], sd = e.psd[i];
         const double ce = K.c_eta[i];
-        const double sv = fma(2.0, v, -1.0);
-        const double phi_p = -e.fph[i] * fma(3.0 * sv, e.rph[i], 2.0);                                  // S5:185-187
-        const double wu = fma(u, u, -u);
-        const double r2 = e.rps[i] * e.rps[i];
-        const double psi_p = (4.0 * K.Kp1) * fma(5.0, wu, 3.0) * (r2 * r2);                              // S5:189
-        const double aii = hrow[i] * A[apk(i, i)];
+        const double hi = (HILL != 0 && i == 4) ? e.h : 1.0;
+        const double aii = hi * A[apk(i, i)];
         const double ap = aii * e.p[i];
         // 2x2 diagonal block of species i (rows i, 6+i; columns i, 6+i), S5:199-245 (+ S5:254-271)
-        const double d00 = phi_p + fma(fma(u, u, K.etaphi_eta[i]), K.inv_dt, u * sd) - ce * u * fma(2.0 * aii, u, e.I[i]);
+        const double d00 = e.phip[i] + fma(fma(u, u, K.etaphi_eta[i]), K.inv_dt, u * sd) - ce * u * fma(2.0 * aii, u, e.I[i]);
         const double d01 = fma(2.0 * u, pd, fma(v, sd, e.p[i] * K.inv_dt)) - ce * fma(3.0, ap, e.I[i]);  // (1/eta) eta = 1
         const double d10 = fma(u, pd, fma(e.p[i], K.inv_dt, 2.0 * v * sd)) - ce * fma(3.0, ap, 2.0 * e.I[i]);
-        double d11 = psi_p + fma(v, pd, v * v * K.inv_dt) - 2.0 * ce * aii * v * v;
+        double d11 = e.psip[i] + fma(v, pd, v * v * K.inv_dt) - 2.0 * ce * aii * v * v;
         if (ALPHA) d11 += b[i] * K.alpha_eta[i];
         // inverse by Cramer with an fma-compensated determinant
         const double t = d01 * d10;
         const double det = fma(d00, d11, -t) + fma(-d01, d10, t);
         const double rdet = 1.0 / det;
         const double r0 = -e.Q[i], r1 = -e.Q[6 + i];
-        a0[i] = fma(d11, r0, -d01 * r1) * rdet;
-        a1[i] = fma(d00, r1, -d10 * r0) * rdet;
+        const double a0 = fma(d11, r0, -d01 * r1) * rdet;
+        const double a1 = fma(d00, r1, -d10 * r0) * rdet;
         const double rdi = rdet * K.inv_eta[i];  // u_i = (1/eta_i, 0): S5:220
-        b0[i] = d11 * rdi;
-        b1[i] = -d10 * rdi;
-        d0[i] = fma(d11, u, -d01 * v) * rdet;
-        d1[i] = fma(d00, v, -d10 * u) * rdet;
+        const double b0 = d11 * rdi;
+        const double b1 = -d10 * rdi;
+        const double dd0 = fma(d11, u, -d01 * v) * rdet;
+        const double dd1 = fma(d00, v, -d10 * u) * rdet;
+        stash[6 * i + 0] = a0;
+        stash[6 * i + 1] = a1;
+        stash[6 * i + 2] = b0;
+        stash[6 * i + 3] = b1;
+        stash[6 * i + 4] = dd0;
+        stash[6 * i + 5] = dd1;
+        // row i of S = I + diag(g) C and its two right-hand sides
+        const double gi = fma(u, dd0, v * dd1) * srow[i];  // q_i^T D_i^{-1} p_i times the row scaling
+#pragma unroll
+        for (int j = 0; j < 5; ++j) S[i][j] = (i == j) ? 1.0 : gi * A[apk(i, j)];
+        if (HILL != 0 && i == 4) S[4][3] = fma(fma(u, dd0, v * dd1), c43x, S[4][3]);
+        S[i][5] = fma(u, a0, v * a1);
+        S[i][6] = fma(u, b0, v * b1);
     }
-    // off-diagonal coefficients C_ij = -c/eta_i h_i A_ij (+ the dh/dx outer product at (4,3), S5:273-287)
-    double Cm[5][5];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        const double s = -K.c_eta[i] * hrow[i];
-#pragma unroll
-        for (int j = 0; j < 5; ++j) Cm[i][j] = (i == j) ? 0.0 : s * A[apk(i, j)];
-    }
-    if (HILL != 0) {
-        if (e.h < 1.0) Cm[4][3] = fma(-K.c_eta[4] * e.Iraw4, e.dh_dx, Cm[4][3]);
-    }
-    auto build_S = [&](double (&T)[5][7]) {
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            const double gi = fma(e.ps[i], d0[i], e.ph[i] * d1[i]);  // q_i^T D_i^{-1} p_i
-#pragma unroll
-            for (int j = 0; j < 5; ++j) T[i][j] = (i == j) ? 1.0 : gi * Cm[i][j];
-            T[i][5] = fma(e.ps[i], a0[i], e.ph[i] * a1[i]);
-            T[i][6] = fma(e.ps[i], b0[i], e.ph[i] * b1[i]);
-        }
-    };
-    build_S(S);
 #if defined(HMX_SOLVE_BLOCK23)
     const double health = solve5x2_block23(S);  // shorter dependency chain, a few more live values; measured 2 % slower
 #else
     const double health = solve5x2_natural(S);
 #endif
-    if (!(health >= kPivotFloor)) {  // rare: rebuild and redo with row pivoting
+    if (!(health >= kPivotFloor)) {  // rare: rebuild the system and redo it with row pivoting
         double T[5][7], X[10];
-        build_S(T);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const double gq = fma(e.ps[i], stash[6 * i + 4], e.ph[i] * stash[6 * i + 5]);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) T[i][j] = (i == j) ? 1.0 : gq * srow[i] * A[apk(i, j)];
+            if (HILL != 0 && i == 4) T[4][3] = fma(gq, c43x, T[4][3]);
+            T[i][5] = fma(e.ps[i], stash[6 * i + 0], e.ph[i] * stash[6 * i + 1]);
+            T[i][6] = fma(e.ps[i], stash[6 * i + 2], e.ph[i] * stash[6 * i + 3]);
+        }
         solve5x2_pivoted(&T[0][0], X);
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
@@ -415,25 +429,30 @@ HMX_HD void direction(const SolverConsts& K, const Eval& e, const AT& A, const d
         }
     }
     // phi_0 row and the constraint row: S5:222-223, 247
-    const double s0v = fma(2.0, e.ph0, -1.0);
-    const double K55 = -e.f0 * fma(3.0 * s0v, e.r0, 2.0) + K.inv_dt;
-    const double rK55 = 1.0 / K55;
+    const double rK55 = 1.0 / e.K55;
     double sumY1 = 0.0, sumY2 = 0.0;
     double y10[5], y11[5], y20[5], y21[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
-        double t1 = 0.0, t2 = 0.0;
+        double t1 = 0.0, t2 = 0.0;  // sum_j C_ij z_j = srow_i sum_j A_ij z_j (+ the (4,3) extra)
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
             if (j != i) {
-                t1 = fma(Cm[i][j], S[j][5], t1);
-                t2 = fma(Cm[i][j], S[j][6], t2);
+                t1 = fma(A[apk(i, j)], S[j][5], t1);
+                t2 = fma(A[apk(i, j)], S[j][6], t2);
             }
         }
-        y10[i] = fma(-d0[i], t1, a0[i]);
-        y11[i] = fma(-d1[i], t1, a1[i]);
-        y20[i] = fma(-d0[i], t2, b0[i]);
-        y21[i] = fma(-d1[i], t2, b1[i]);
+        t1 *= srow[i];
+        t2 *= srow[i];
+        if (HILL != 0 && i == 4) {
+            t1 = fma(c43x, S[3][5], t1);
+            t2 = fma(c43x, S[3][6], t2);
+        }
+        const double dd0 = stash[6 * i + 4], dd1 = stash[6 * i + 5];
+        y10[i] = fma(-dd0, t1, stash[6 * i + 0]);
+        y11[i] = fma(-dd1, t1, stash[6 * i + 1]);
+        y20[i] = fma(-dd0, t2, stash[6 * i + 2]);
+        y21[i] = fma(-dd1, t2, stash[6 * i + 3]);
         sumY1 += y10[i];
         sumY2 += y20[i];
     }
@@ -446,6 +465,13 @@ HMX_HD void direction(const SolverConsts& K, const Eval& e, const AT& A, const d
     }
     delta[5] = (-e.Q[5] - dgam) * rK55;
     delta[11] = dgam;
+}
+
+// convenience overload with a register-array stash (host emulation, observation kernel)
+template <bool ALPHA, int HILL, class AT, class DT>
+HMX_HD void direction(const SolverConsts& K, const Eval& e, const AT& A, const double (&b)[5], DT& delta) {
+    RegStash st;
+    direction<ALPHA, HILL>(K, e, A, b, delta, st);
 }
 
 }  // namespace hmx
