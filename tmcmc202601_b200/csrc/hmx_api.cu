@@ -517,7 +517,7 @@ int hmx_resample(hmx_ctx* ctx, const double* w, int64_t N, double u, int64_t* id
     if ((rc = stage_in(ctx, w, (size_t)N * sizeof(double), ctx->st_in0, &d_w))) return rc;
     if ((rc = stage_out(ctx, idx, (size_t)N * sizeof(int64_t), ctx->st_out0, &d_idx, &h_idx))) return rc;
     if ((rc = ensure(ctx, ctx->cs, (size_t)N * sizeof(double)))) return rc;
-    cumsum_serial_kernel<<<1, 32, 0, ctx->stream>>>((const double*)d_w, N, (double*)ctx->cs.p);
+    cumsum_serial_kernel<<<1, kRedThreads, 0, ctx->stream>>>((const double*)d_w, N, (double*)ctx->cs.p);
     searchsorted_kernel<<<red_blocks(N), kRedThreads, 0, ctx->stream>>>((const double*)ctx->cs.p, N, u, (long long*)d_idx);
     CU(cudaGetLastError());
     ctx->launches += 2;

@@ -177,21 +177,40 @@ __global__ void __launch_bounds__(kRedThreads) weights_norm_kernel(double* __res
 }
 
 // K4a: cs = np.cumsum(w) with the exact left-to-right association, cs[N-1] := 1.0  (TM:195-197).
-// One warp: coalesced loads of 32 elements, the running sum travels lane to lane through shuffles.
-__global__ void __launch_bounds__(32) cumsum_serial_kernel(const double* __restrict__ w, long long N, double* __restrict__ cs) {
-    const int lane = threadIdx.x;
+// The running sum is one chain of N dependent FP64 adds (any re-association could move a resampling index), so
+// the floor is N x DADD latency.  One CTA: all threads stage a tile of w in shared memory (coalesced), thread 0
+// walks the tile with the carry in a register (operands come from shared memory, off the dependency chain),
+// all threads write the prefixes back (coalesced).
+constexpr int kCumsumTile = 4096;
+__global__ void __launch_bounds__(kRedThreads) cumsum_serial_kernel(const double* __restrict__ w, long long N, double* __restrict__ cs) {
+    __shared__ double tile[kCumsumTile];
     double carry = 0.0;
-    for (long long base = 0; base < N; base += 32) {
-        const long long i = base + lane;
-        const double x = (i < N) ? w[i] : 0.0;
-        double mine = 0.0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const double xj = __shfl_sync(0xffffffffu, x, j);
-            carry = carry + xj;  // same value in every lane; lane j keeps the prefix ending at element j
-            if (lane == j) mine = carry;
+    for (long long base = 0; base < N; base += kCumsumTile) {
+        const int n = (int)((N - base < kCumsumTile) ? (N - base) : kCumsumTile);
+        for (int t = threadIdx.x; t < n; t += blockDim.x) tile[t] = w[base + t];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (; t + 8 <= n; t += 8) {
+                const double x0 = tile[t], x1 = tile[t + 1], x2 = tile[t + 2], x3 = tile[t + 3];
+                const double x4 = tile[t + 4], x5 = tile[t + 5], x6 = tile[t + 6], x7 = tile[t + 7];
+                carry = __dadd_rn(carry, x0); tile[t] = carry;
+                carry = __dadd_rn(carry, x1); tile[t + 1] = carry;
+                carry = __dadd_rn(carry, x2); tile[t + 2] = carry;
+                carry = __dadd_rn(carry, x3); tile[t + 3] = carry;
+                carry = __dadd_rn(carry, x4); tile[t + 4] = carry;
+                carry = __dadd_rn(carry, x5); tile[t + 5] = carry;
+                carry = __dadd_rn(carry, x6); tile[t + 6] = carry;
+                carry = __dadd_rn(carry, x7); tile[t + 7] = carry;
+            }
+            for (; t < n; ++t) {
+                carry = __dadd_rn(carry, tile[t]);
+                tile[t] = carry;
+            }
         }
-        if (i < N) cs[i] = (i == N - 1) ? 1.0 : mine;
+        __syncthreads();
+        for (int t = threadIdx.x; t < n; t += blockDim.x) cs[base + t] = (base + t == N - 1) ? 1.0 : tile[t];
+        __syncthreads();
     }
 }
 
