@@ -211,12 +211,11 @@ HMX_HD void residual(const SolverConsts& K, const double (&x)[12], const GPT& gp
         }
         e.I[4] *= e.h;
     }
-    double nrm = 0.0, asum = 0.0;
+    double nr[6], as[6];  // per-row partial max / sum of |Q|: reduced as trees to keep the dependency chain short
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
         const double v = e.ph[i], u = e.ps[i];
-        // Q_i, S5:98-106
-        // (1/eta)[gamma + (eta_phi + eta psi^2) phidot + eta phi psi psidot], with 1/eta distributed
+        // Q_i, S5:98-106: (1/eta)[gamma + (eta_phi + eta psi^2) phidot + eta phi psi psidot], 1/eta distributed
         const double t2 = fma(K.inv_eta[i], gam, fma(fma(u, u, K.etaphi_eta[i]), e.phd[i], e.p[i] * e.psd[i]));
         const double qi = fph[i] + t2 - K.c_eta[i] * u * e.I[i];
         // Q_{6+i}, S5:116-123
@@ -224,14 +223,15 @@ HMX_HD void residual(const SolverConsts& K, const double (&x)[12], const GPT& gp
         if (ALPHA) qs += (b[i] * K.alpha_eta[i]) * u;
         e.Q[i] = qi;
         e.Q[6 + i] = qs;
-        nrm = fmax(nrm, fmax(fabs(qi), fabs(qs)));
-        asum += fabs(qi) + fabs(qs);
+        nr[i] = fmax(fabs(qi), fabs(qs));
+        as[i] = fabs(qi) + fabs(qs);
     }
     e.Q[5] = gam + f0 + (ph0 - gp[5]) * K.inv_dt;                                  // S5:109-113
     e.Q[11] = ((((e.ph[0] + e.ph[1]) + e.ph[2]) + e.ph[3]) + e.ph[4]) + ph0 - 1.0;    // S5:126
-    nrm = fmax(nrm, fmax(fabs(e.Q[5]), fabs(e.Q[11])));
-    asum += fabs(e.Q[5]) + fabs(e.Q[11]);
-    e.norm = nrm;
+    nr[5] = fmax(fabs(e.Q[5]), fabs(e.Q[11]));
+    as[5] = fabs(e.Q[5]) + fabs(e.Q[11]);
+    e.norm = fmax(fmax(fmax(nr[0], nr[1]), fmax(nr[2], nr[3])), fmax(nr[4], nr[5]));
+    const double asum = ((as[0] + as[1]) + (as[2] + as[3])) + (as[4] + as[5]);
     e.nan = (asum != asum);  // true for NaN only (a sum of |.| is +inf, not NaN, for infinite entries): S5:342-348
 }
 
@@ -472,9 +472,9 @@ HMX_HD void direction(const SolverConsts& K, const Eval& e, const AT& A, const d
         y11[i] = fma(-dd1, t1, stash[6 * i + 1]);
         y20[i] = fma(-dd0, t2, stash[6 * i + 2]);
         y21[i] = fma(-dd1, t2, stash[6 * i + 3]);
-        sumY1 += y10[i];
-        sumY2 += y20[i];
     }
+    sumY1 = ((y10[0] + y10[1]) + (y10[2] + y10[3])) + y10[4];
+    sumY2 = ((y20[0] + y20[1]) + (y20[2] + y20[3])) + y20[4];
     const double srhs = fma(e.Q[5], rK55, -e.Q[11]);
     const double dgam = (sumY1 - srhs) * rcp(sumY2 + rK55);
 #pragma unroll
