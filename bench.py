@@ -47,12 +47,15 @@ METRIC = "particle_ode_likelihood_evals_per_sec"
 UNIT = "evals/s"
 
 # Executed FP64 flops (DFMA = 2, DMUL = DADD = 1) of the ODE kernel per residual evaluation ("trip") and per
-# quasi-Newton direction solve, calibrated from the ncu capture profiles/r01b_ode_kernel_large_batch.json
-# (thread-level sass op counters: 1.8806e12 DFMA + 1.2143e12 DMUL + 3.584e11 DADD thread-instructions for the
-# kernel's own counters of 4.5913e9 residual evaluations and 3.4175e9 directions; split between the two by the
-# static SASS ratio of residual() : direction() = 443 : 1287).  DESIGN.md "Roofline accounting" has the derivation.
-FLOPS_PER_RESIDUAL = 367.0
-FLOPS_PER_DIRECTION = 1067.0
+# quasi-Newton direction solve, calibrated from the ncu capture profiles/r01f_ode_kernel_rcp_lean.json
+# (thread-level sass op counters: 1.7576e12 DFMA + 1.1418e12 DMUL + 3.481e11 DADD thread-instructions =
+# 5.005e12 flop for the kernel's own counters of 4.5913e9 residual evaluations and 3.4175e9 directions; split
+# between the two by the static SASS count of residual() : direction() = 441 : 820 flops, scale 1.037).
+# DESIGN.md "Roofline accounting" has the derivation.
+FLOPS_PER_RESIDUAL = 457.0
+FLOPS_PER_DIRECTION = 850.0
+# DRAM bytes per evaluation of the same capture (dram__bytes_read.sum + dram__bytes_write.sum) / 262144
+DRAM_BYTES_PER_EVAL_NCU = 1134.0
 # the reference-equivalent count of SURVEY.md section 8(d): dense Q + K + dgesv per iteration, Q per extra trial
 REF_FLOPS_PER_ITER = 2778.0
 REF_FLOPS_PER_TRIAL = 384.0
@@ -350,7 +353,8 @@ def main():
                  / (ode_avg_ms * 1e-3) / 1e12)
     roofline = {
         "bound": "fp64", "kernel": "hmx::ode_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-        "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+        "frac": achieved / fp64_peak if fp64_peak > 0 else None,
+        "traffic": DRAM_BYTES_PER_EVAL_NCU * M,  # bytes per launch; ncu measured 1134 B/evaluation, algorithmic 1144
         "peak_source": "measured live by hmx_measure_fp64_peak (register-resident DFMA loop); MEASURED_PEAKS.json has no FP64 entry "
                        "(nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2)",
         "kernel_ms_per_launch": ode_avg_ms, "kernel_share_of_step": ode_avg_ms * args.steps / elapsed_ms,
