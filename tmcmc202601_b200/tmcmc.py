@@ -148,16 +148,36 @@ def systematic_resample(weights: np.ndarray, rng: np.random.Generator, stage_ops
 
 
 def reflect_into_bounds(x, low, high):
-    """Fold x into [low, high] by reflection; width <= 0 clips (TM:201-226).  Works on scalars and arrays."""
-    x = np.asarray(x, dtype=np.float64)
+    """Fold x into [low, high] by reflection; width <= 0 clips (TM:201-226).  Works on scalars and arrays.
+
+    Same arithmetic as the reference's scalar function, `low + fold((x - low) % (2 width))`, but the modulo
+    (exact, hence the identity for 0 <= x - low < 2 width) is only evaluated where it can change the value."""
+    scalar = np.ndim(x) == 0
+    x = np.atleast_1d(np.asarray(x, dtype=np.float64))
     low = np.asarray(low, dtype=np.float64)
     high = np.asarray(high, dtype=np.float64)
-    width = high - low
-    safe = np.where(width > 0, width, 1.0)
-    y = (x - low) % (2 * safe)
-    y = np.where(y > safe, 2 * safe - y, y)
-    out = np.where(width > 0, low + y, np.clip(x, low, high))
-    return float(out) if out.ndim == 0 else out
+    if x.ndim == 2 and x.shape[0] > 32768:  # cache-sized row blocks: the passes below are memory bound
+        out = np.empty_like(x)
+        for a in range(0, x.shape[0], 16384):
+            out[a:a + 16384] = reflect_into_bounds(x[a:a + 16384], low, high)
+        return out
+    width = np.broadcast_to(high - low, x.shape)
+    lowb = np.broadcast_to(low, x.shape)
+    y = x - lowb
+    two_w = 2.0 * width
+    far = (y < 0.0) | (y >= two_w)
+    far &= width > 0
+    if far.any():
+        y[far] = np.mod(y[far], two_w[far])
+    over = y > width
+    over &= width > 0
+    if over.any():
+        y[over] = two_w[over] - y[over]
+    y += lowb
+    degenerate = width <= 0
+    if degenerate.any():
+        y[degenerate] = np.clip(x, lowb, np.broadcast_to(high, x.shape))[degenerate]
+    return float(y[0]) if scalar else y
 
 
 def evaluate_particles_parallel(log_likelihood: Callable, theta: np.ndarray, n_jobs: Optional[int] = None,
