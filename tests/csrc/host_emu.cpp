@@ -19,21 +19,18 @@ static void run_lane(const SolverConsts& K, const CondConsts& C, const ThetaMap&
     if (g_arr) memcpy(g_arr, s.g, 12 * sizeof(double));
     double pairs[HMX_MAX_OBS * kPairStride];
     memset(pairs, 0, sizeof(pairs));
-    bool done = false;
-    while (!done) {
-        if (lane_trip<ALPHA, HILL>(K, s)) {
-            double old[11];
-            for (int i = 0; i < 11; ++i) old[i] = s.gp[i];
-            done = lane_advance(K, s);
-            if (g_arr) memcpy(g_arr + (size_t)s.step_idx * 12, s.g, 12 * sizeof(double));
-            for (int o = 0; o < C.n_obs; ++o) {
-                const int t = C.idx[o] < 1 ? 1 : C.idx[o];
-                if (t == s.step_idx) {
-                    memcpy(pairs + o * kPairStride, s.g, 12 * sizeof(double));
-                    memcpy(pairs + o * kPairStride + 12, old, 11 * sizeof(double));
-                }
+    auto step_end = [&](const Lane& l) {  // l.g = g_arr[step_idx + 1], l.gp = g_arr[step_idx]
+        const int row = l.step_idx + 1;
+        if (g_arr) memcpy(g_arr + (size_t)row * 12, l.g, 12 * sizeof(double));
+        for (int o = 0; o < C.n_obs; ++o) {
+            const int t = C.idx[o] < 1 ? 1 : C.idx[o];
+            if (t == row) {
+                memcpy(pairs + o * kPairStride, l.g, 12 * sizeof(double));
+                for (int i = 0; i < 11; ++i) pairs[o * kPairStride + 12 + i] = l.gp[i];
             }
         }
+    };
+    while (!lane_trip<ALPHA, HILL>(K, s, step_end)) {
     }
     uint32_t st = s.status;
     if (logL) *logL = obs_loglik<ALPHA, HILL>(K, C, TM, theta, pairs, s.status, nullptr, &st);

@@ -132,7 +132,7 @@ def test_lane_state_machine_matches_oracle(key):
         rel = np.abs(g - go) / np.maximum(np.abs(go), 1e-300)
         assert rel.max() < 1e-9, rel.max()
         assert it.value == its  # same quasi-Newton iterate sequence
-        assert tr.value >= its + cfg.n_steps  # one residual per iteration start + trials
+        assert trials < tr.value <= trials + its  # the line-search trials + the few full iteration-start residuals (step starts are rebased)
         assert abs(ll.value - llo) <= 1e-9 * abs(llo)
         assert (st.value & 1) == (sto & 1)
 
