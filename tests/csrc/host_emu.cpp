@@ -19,14 +19,14 @@ static void run_lane(const SolverConsts& K, const CondConsts& C, const ThetaMap&
     if (g_arr) memcpy(g_arr, s.g, 12 * sizeof(double));
     double pairs[HMX_MAX_OBS * kPairStride];
     memset(pairs, 0, sizeof(pairs));
-    auto step_end = [&](const Lane& l) {  // l.g = g_arr[step_idx + 1], l.gp = g_arr[step_idx]
-        const int row = l.step_idx + 1;
-        if (g_arr) memcpy(g_arr + (size_t)row * 12, l.g, 12 * sizeof(double));
+    auto step_end = [&](const double (&g)[12], const LaneGP& gp, int step_idx) {  // g = g_arr[step_idx + 1], gp = g_arr[step_idx]
+        const int row = step_idx + 1;
+        if (g_arr) memcpy(g_arr + (size_t)row * 12, g, 12 * sizeof(double));
         for (int o = 0; o < C.n_obs; ++o) {
             const int t = C.idx[o] < 1 ? 1 : C.idx[o];
             if (t == row) {
-                memcpy(pairs + o * kPairStride, l.g, 12 * sizeof(double));
-                for (int i = 0; i < 11; ++i) pairs[o * kPairStride + 12 + i] = l.gp[i];
+                memcpy(pairs + o * kPairStride, g, 12 * sizeof(double));
+                for (int i = 0; i < 11; ++i) pairs[o * kPairStride + 12 + i] = gp[i];
             }
         }
     };

@@ -119,27 +119,27 @@ __global__ void HMX_ODE_BOUNDS ode_kernel(const __grid_constant__ OdeParams P) {
             next_t = (P.cond[c].n_obs > 0) ? max(P.cond[c].idx[0], 1) : 0x7fffffff;
             have = true;
         }
-        // end of a time step (called from inside the trip): s.g = g_arr[step_idx + 1], s.gp = g_arr[step_idx]
-        auto step_end = [&](const Lane& l) {
-            if (l.step_idx + 1 == next_t) {
+        // end of a time step (called from inside the trip): g = g_arr[step_idx + 1], gp = g_arr[step_idx]
+        auto step_end = [&](const double (&g)[12], const LaneGP& gp, int step_idx) {
+            if (step_idx + 1 == next_t) {
                 // observation row reached: keep (g_t, g_{t-1}) for the sensitivity kernel
                 const OdeCond& oc = P.cond[c];
                 double* pr = P.pairs + w * P.pair_stride;
                 do {
                     double* q = pr + next_obs * kPairStride;
 #pragma unroll
-                    for (int i = 0; i < 12; ++i) q[i] = l.g[i];
+                    for (int i = 0; i < 12; ++i) q[i] = g[i];
 #pragma unroll
-                    for (int i = 0; i < 11; ++i) q[12 + i] = l.gp[i];
+                    for (int i = 0; i < 11; ++i) q[12 + i] = gp[i];
                     q[23] = 0.0;
                     ++next_obs;
                     next_t = (next_obs < oc.n_obs) ? max(oc.idx[next_obs], 1) : 0x7fffffff;
-                } while (l.step_idx + 1 == next_t);
+                } while (step_idx + 1 == next_t);
             }
             if (P.traj) {
-                double* q = P.traj + w * (long long)(P.K.n_steps + 1) * 12 + (long long)(l.step_idx + 1) * 12;
+                double* q = P.traj + w * (long long)(P.K.n_steps + 1) * 12 + (long long)(step_idx + 1) * 12;
 #pragma unroll
-                for (int i = 0; i < 12; ++i) q[i] = l.g[i];
+                for (int i = 0; i < 12; ++i) q[i] = g[i];
             }
         };
         if (lane_trip<ALPHA, HILL>(P.K, s, step_end)) {

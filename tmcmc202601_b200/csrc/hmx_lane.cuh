@@ -112,8 +112,16 @@ HMX_HD void lane_init(const SolverConsts& K, Lane& s, const double* theta, const
     s.tol = step_tol(K, 0);
 }
 
-// Bookkeeping after a finished time step: s.g becomes the new previous level.
-// Returns true when all n_steps levels are done.
+// Bookkeeping after a finished time step.  Returns true when all n_steps levels are done.
+HMX_HD bool lane_next_level(const SolverConsts& K, Lane& s) {
+    ++s.step_idx;
+    s.it = 0;
+    s.mode = kModeEval;
+    s.tol = step_tol(K, s.step_idx);
+    return s.step_idx >= K.n_steps;
+}
+
+// ... including the hand-over s.g -> previous level and the isfinite scan of the new trajectory row.
 HMX_HD bool lane_advance(const SolverConsts& K, Lane& s) {
     double chk = 0.0;
 #pragma unroll
@@ -121,11 +129,7 @@ HMX_HD bool lane_advance(const SolverConsts& K, Lane& s) {
     if (chk != 0.0) s.status |= kStNonfinite;  // EV:657-667 scans the whole trajectory
 #pragma unroll
     for (int i = 0; i < 11; ++i) s.gp[i] = s.g[i];
-    ++s.step_idx;
-    s.it = 0;
-    s.mode = kModeEval;
-    s.tol = step_tol(K, s.step_idx);
-    return s.step_idx >= K.n_steps;
+    return lane_next_level(K, s);
 }
 
 // First residual of the NEXT time step, derived from the residual of the accepted trial that just ended the
@@ -138,7 +142,7 @@ HMX_HD bool lane_advance(const SolverConsts& K, Lane& s) {
 // residual evaluation per time step (2500 of ~17500 per solve) by ~60 flops, and it turns the trip that detects
 // convergence into a trip that also computes the next step's first direction.
 // x: the raw accepted trial (== s.g == new s.gp); gp5_old: phi_0 of the previous level before the advance.
-HMX_HD void rebase_residual(const SolverConsts& K, const Lane& s, const double (&x)[12], double gp5_old, Eval& e) {
+HMX_HD bool rebase_residual(const SolverConsts& K, const Lane& s, const double (&x)[12], double gp5_old, Eval& e) {
     double nr[6], as[6];
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
@@ -151,21 +155,23 @@ HMX_HD void rebase_residual(const SolverConsts& K, const Lane& s, const double (
         const double qs = e.Q[6 + i] + fma(e.p[i], dph, v * v * dps);
         e.Q[i] = qi;
         e.Q[6 + i] = qs;
-        nr[i] = fmax(fabs(qi), fabs(qs));
+        nr[i] = max_abs(qi, qs);
         as[i] = fabs(qi) + fabs(qs);
     }
     const double ph0 = clip01(x[5]);
     e.Q[5] = e.Q[5] + ((ph0 - s.gp[5]) - (ph0 - gp5_old)) * K.inv_dt;
-    nr[5] = fmax(fabs(e.Q[5]), fabs(e.Q[11]));
+    nr[5] = max_abs(e.Q[5], e.Q[11]);
     as[5] = fabs(e.Q[5]) + fabs(e.Q[11]);
-    e.norm = fmax(fmax(fmax(nr[0], nr[1]), fmax(nr[2], nr[3])), fmax(nr[4], nr[5]));
+    e.norm = max_abs(max_abs(max_abs(nr[0], nr[1]), max_abs(nr[2], nr[3])), max_abs(nr[4], nr[5]));
     const double asum = ((as[0] + as[1]) + (as[2] + as[3])) + (as[4] + as[5]);
     e.nan = (asum != asum);
+    // A non-finite component of x makes (clip(x) - x)/dt, hence the sum, non-finite (gamma entered the accepted
+    // residual itself, which was finite): this test doubles as the trajectory's isfinite scan (EV:657-667).
+    return asum <= 1.7976931348623157e308;
 }
 
-// One trip.  `step_end(s)` is called whenever the Newton loop of the current time step has ended, with
-// s.g = g_arr[step_idx + 1] and s.gp = g_arr[step_idx]; the lane then advances to the next time level by
-// itself.  Returns true when all n_steps levels are done.
+// One trip.  `step_end(g, gp, step_idx)` is called whenever the Newton loop of the current time step has ended,
+// with g = g_arr[step_idx + 1] and gp = g_arr[step_idx]; the lane then advances to the next time level by itself.  Returns true when all n_steps levels are done.
 template <bool ALPHA, int HILL, class StepEnd>
 HMX_HD bool lane_trip(const SolverConsts& K, Lane& s, StepEnd&& step_end) {
     double x[12];
@@ -213,10 +219,6 @@ HMX_HD bool lane_trip(const SolverConsts& K, Lane& s, StepEnd&& step_end) {
             }
         }
     }
-    if (take_raw) {
-#pragma unroll
-        for (int i = 0; i < 12; ++i) s.g[i] = x[i];
-    }
     if (take_clipped) {
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
@@ -229,24 +231,42 @@ HMX_HD bool lane_trip(const SolverConsts& K, Lane& s, StepEnd&& step_end) {
     bool done = false;
     if (finished) {
         if (!nan_break && !(s.normQ < s.tol)) s.status |= kStMaxIter;  // range(max_newton_iter) exhausted
-        const double gp5_old = s.gp[5];
-        step_end(s);
-        done = lane_advance(K, s);
 #if !defined(HMX_NO_REBASE)
-        if (take_raw && !done) {
-            rebase_residual(K, s, x, gp5_old, e);
-            if (!e.nan) {  // (a NaN here takes the ordinary path: full residual on the next trip, S5:342-348)
+        if (take_raw) {
+            // the common way out of a time step: an accepted trial x, which is g_arr[step_idx + 1] unclipped
+            step_end(x, s.gp, s.step_idx);
+            const double gp5_old = s.gp[5];
+#pragma unroll
+            for (int i = 0; i < 11; ++i) s.gp[i] = x[i];
+            done = lane_next_level(K, s);
+            const bool finite = rebase_residual(K, s, x, gp5_old, e);
+            if (!finite) s.status |= kStNonfinite;
+            if (finite && !done) {
                 s.normQ = e.norm;
 #pragma unroll
                 for (int i = 0; i < 5; ++i) {  // clipped write-back at the start of the new step's first iteration
                     s.g[i] = e.ph[i];
                     s.g[6 + i] = e.ps[i];
                 }
+                s.g[5] = x[5];
+                s.g[11] = x[11];
                 need_dir = true;
                 ++s.rebased;
+            } else {  // ordinary path: full residual at x on the next trip (S5:342-348 handles a NaN there)
+#pragma unroll
+                for (int i = 0; i < 12; ++i) s.g[i] = x[i];
             }
-        }
+        } else
 #endif
+        {
+            // NaN residual at an iteration start, no improving step length at the tolerance / iteration limit
+            if (take_raw) {
+#pragma unroll
+                for (int i = 0; i < 12; ++i) s.g[i] = x[i];
+            }
+            step_end(s.g, s.gp, s.step_idx);
+            done = lane_advance(K, s);
+        }
     }
     // All lanes of the warp meet here before the direction solve.  Without the barrier the compiler lets the
     // lanes that skipped the step-end block run ahead, and the warp executes the (expensive) solve twice:

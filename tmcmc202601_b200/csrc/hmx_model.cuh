@@ -78,6 +78,13 @@ HMX_HD double clip01(double v) {
     return (v < kClipLo) ? kClipLo : ((v > kClipHi) ? kClipHi : v);
 }
 
+// max(|a|, |b|) as one ordered compare and a select.  fmax() costs twice the instructions because of its NaN
+// rules; the callers detect NaN separately (sum of |Q|) and never use the maximum when one is present.
+HMX_HD double max_abs(double a, double b) {
+    const double fa = fabs(a), fb = fabs(b);
+    return (fa > fb) ? fa : fb;
+}
+
 // packed symmetric A: index of (i,j)
 HMX_HD constexpr int apk(int i, int j) {
     return (i <= j) ? (i * 5 - (i * (i - 1)) / 2 + (j - i)) : (j * 5 - (j * (j - 1)) / 2 + (i - j));
@@ -223,14 +230,14 @@ HMX_HD void residual(const SolverConsts& K, const double (&x)[12], const GPT& gp
         if (ALPHA) qs += (b[i] * K.alpha_eta[i]) * u;
         e.Q[i] = qi;
         e.Q[6 + i] = qs;
-        nr[i] = fmax(fabs(qi), fabs(qs));
+        nr[i] = max_abs(qi, qs);
         as[i] = fabs(qi) + fabs(qs);
     }
     e.Q[5] = gam + f0 + (ph0 - gp[5]) * K.inv_dt;                                  // S5:109-113
     e.Q[11] = ((((e.ph[0] + e.ph[1]) + e.ph[2]) + e.ph[3]) + e.ph[4]) + ph0 - 1.0;    // S5:126
-    nr[5] = fmax(fabs(e.Q[5]), fabs(e.Q[11]));
+    nr[5] = max_abs(e.Q[5], e.Q[11]);
     as[5] = fabs(e.Q[5]) + fabs(e.Q[11]);
-    e.norm = fmax(fmax(fmax(nr[0], nr[1]), fmax(nr[2], nr[3])), fmax(nr[4], nr[5]));
+    e.norm = max_abs(max_abs(max_abs(nr[0], nr[1]), max_abs(nr[2], nr[3])), max_abs(nr[4], nr[5]));
     const double asum = ((as[0] + as[1]) + (as[2] + as[3])) + (as[4] + as[5]);
     e.nan = (asum != asum);  // true for NaN only (a sum of |.| is +inf, not NaN, for infinite entries): S5:342-348
 }
