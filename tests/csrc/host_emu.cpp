@@ -54,6 +54,40 @@ static void dir_once(const SolverConsts& K, const double* theta, const double* g
     for (int i = 0; i < 12; ++i) delta[i] = d[i];
 }
 
+// rebase_residual() against a fresh residual: x is the accepted trial that ended a step whose previous level
+// was g_old; the next step's first residual is Q(clip(x); previous level = x).
+template <bool ALPHA, int HILL>
+static void rebase_once(const SolverConsts& K, const double* theta, const double* x_in, const double* g_old,
+                        double* Q_rebased, double* Q_direct, double* norms, int* finite) {
+    Lane s;
+    double x[12], xc[12];
+    theta_to_Ab(theta, s.A, s.b);
+    for (int i = 0; i < 12; ++i) x[i] = x_in[i];
+    for (int i = 0; i < 11; ++i) s.gp[i] = g_old[i];
+    Eval e;
+    residual<ALPHA, HILL>(K, x, s.gp, s.A, s.b, e);
+    const double gp5_old = s.gp[5];
+    for (int i = 0; i < 11; ++i) s.gp[i] = x[i];
+    *finite = rebase_residual(K, s, x, gp5_old, e) ? 1 : 0;
+    for (int i = 0; i < 12; ++i) Q_rebased[i] = e.Q[i];
+    norms[0] = e.norm;
+    // what the ordinary path evaluates on the next trip: iterate = x, previous level = x
+    for (int i = 0; i < 12; ++i) xc[i] = x[i];
+    Eval f;
+    residual<ALPHA, HILL>(K, xc, s.gp, s.A, s.b, f);
+    for (int i = 0; i < 12; ++i) Q_direct[i] = f.Q[i];
+    norms[1] = f.norm;
+    // the direction solve must see identical inputs apart from Q
+    double dev = 0.0;
+    for (int i = 0; i < 5; ++i) {
+        dev = fmax(dev, fabs(e.phd[i] - f.phd[i]));
+        dev = fmax(dev, fabs(e.psd[i] - f.psd[i]));
+        dev = fmax(dev, fabs(e.ph[i] - f.ph[i]) + fabs(e.ps[i] - f.ps[i]) + fabs(e.I[i] - f.I[i]));
+        dev = fmax(dev, fabs(e.phip[i] - f.phip[i]) + fabs(e.psip[i] - f.psip[i]));
+    }
+    norms[2] = dev + fabs(e.K55 - f.K55) + fabs(e.h - f.h);
+}
+
 #define DISPATCH(FN, ...)                                   \
     do {                                                    \
         const bool al = (K.alpha != 0.0);                   \
@@ -82,6 +116,14 @@ int emu_evaluate(const hmx_config* cfg, int cond, const double* theta, double* g
     make_cond_consts(*cfg, cond, C);
     ThetaMap TM = {HMX_THETA_P, HMX_THETA_Q};
     DISPATCH(run_lane, K, C, TM, theta, g_arr, logL, status, iters, trips);
+    return 0;
+}
+
+int emu_rebase(const hmx_config* cfg, const double* theta, const double* x, const double* g_old,
+               double* Q_rebased, double* Q_direct, double* norms, int* finite) {
+    SolverConsts K;
+    make_solver_consts(*cfg, K);
+    DISPATCH(rebase_once, K, theta, x, g_old, Q_rebased, Q_direct, norms, finite);
     return 0;
 }
 

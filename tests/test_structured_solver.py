@@ -70,6 +70,41 @@ def test_direction_equals_dense_lapack_solve(extra):
     assert worst_d < 1e-9, worst_d  # observed <= 1e-12 with cond(K) ~ 1e8
 
 
+@pytest.mark.parametrize("extra", CONFIGS[:4], ids=lambda d: f"K{d['K_hill']}_n{d['n_hill']}_a{d['alpha_const']}")
+def test_rebased_step_start_residual_equals_fresh_evaluation(extra):
+    """The residual a new time step starts with, derived from the accepted trial's residual (rebase_residual),
+    equals a fresh evaluation at the same point -- including trials that left the [1e-12, 1-1e-12] box, where
+    the new time derivatives (clip(x) - x)/dt are not zero -- up to rounding of the largest term of Q."""
+    cd = workloads.load_conditions()["Dysbiotic_HOBIC"]
+    kw = dict(dt=1e-4, maxtimestep=2500, Kp1=1e-4, eta_vec=[1.0, 1.3, 0.8, 1.1, 0.9], eta_phi_vec=[1.2, 0.7, 1.0, 1.5, 0.95], **extra)
+    cfg = _abi.make_config([workloads.cond_struct(cd)], **kw)
+    b = np.array(cd["bounds"])
+    rng = np.random.default_rng(21)
+    for j in range(120):
+        th = rng.uniform(b[:, 0], b[:, 1])
+        g_old = np.concatenate([rng.uniform(1e-3, 0.3, 5), [0.1], rng.uniform(0.2, 0.999, 5), [rng.normal() * 10]])
+        x = g_old + rng.normal(size=12) * np.array([1e-4] * 11 + [0.1])
+        if j % 3 == 0:
+            x[rng.integers(0, 5)] = -rng.uniform(0, 1e-5)      # phi below the box
+        if j % 4 == 0:
+            x[6 + rng.integers(0, 5)] = 1.0 + rng.uniform(0, 1e-5)  # psi above the box
+        if j % 5 == 0:
+            x[5] = -1e-6                                       # phi_0 is clipped inside Q only
+        Qr, Qd, norms, fin = np.zeros(12), np.zeros(12), np.zeros(3), C.c_int()
+        emu.emu_rebase(C.byref(cfg), dptr(th), dptr(x), dptr(g_old), dptr(Qr), dptr(Qd), dptr(norms), C.byref(fin))
+        assert fin.value == 1
+        scale = max(np.abs(Qd).max(), 1.0 / 1e-4)  # terms of size |x|/dt cancel inside Q
+        assert np.max(np.abs(Qr - Qd)) <= 1e-12 * scale, (j, np.max(np.abs(Qr - Qd)), scale)
+        assert abs(norms[0] - norms[1]) <= 1e-12 * scale
+        assert norms[2] == 0.0  # everything else the direction solve reads is bitwise the same
+    # a non-finite component must be reported (it doubles as the trajectory's isfinite scan)
+    for k in (0, 5, 7):
+        x = g_old.copy()
+        x[k] = np.inf if k != 7 else np.nan
+        emu.emu_rebase(C.byref(cfg), dptr(th), dptr(x), dptr(g_old), dptr(Qr), dptr(Qd), dptr(norms), C.byref(fin))
+        assert fin.value == 0, k
+
+
 def test_solve5x2_natural_and_pivoted_agree_with_numpy():
     rng = np.random.default_rng(11)
     for trial in range(50):
