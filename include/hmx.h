@@ -151,7 +151,9 @@ int hmx_log_likelihood_sparse(hmx_ctx* ctx, const double* mu, const double* sig,
 typedef struct {
     int64_t evals;         /* evaluations processed by the last hmx_loglik_batch / hmx_trajectory_batch */
     int64_t newton_iters;  /* sum of quasi-Newton iterations (direction solves) */
-    int64_t q_evals;       /* residual evaluations = state-machine trips (iteration starts + line-search trials) */
+    int64_t q_evals;       /* full residual evaluations = state-machine trips (line-search trials + the iteration starts that
+                              cannot reuse a trial's residual; the first residual of a time step is derived from the accepted
+                              trial that ended the previous one and is not counted) */
     int64_t kernel_launches; /* CUDA kernels launched by this context since creation */
     double last_ode_kernel_ms; /* CUDA-event duration of the ODE kernel of the last batch (0 if not timed) */
 } hmx_counters;
@@ -161,6 +163,41 @@ int hmx_get_counters(hmx_ctx* ctx, hmx_counters* out);
 int hmx_set_timing(hmx_ctx* ctx, int32_t enabled);
 /* register-resident DFMA loop: measured FP64 FMA peak of this GPU in TFLOP/s (roofline denominator) */
 int hmx_measure_fp64_peak(hmx_ctx* ctx, double* tflops);
+
+/* ---- device-side MH mutation of one TMCMC stage ---------------------------------------------------------------
+ * Replaces the proposal / evaluate / accept block of run_TMCMC's `mutate` (core/tmcmc.py:849-962) for the Gaussian
+ * proposal: for each of the N resampled particles, K proposals mean_i + factor z (z ~ N(0, I_d), Philox4x32-10),
+ * reflected into [low, high] (tmcmc.py:201-226), mapped to the 20-vector of the ODE (evaluator.py:631-637), solved
+ * by the same kernels as hmx_loglik_batch, and accepted sequentially with log u < beta (logL' - logL)
+ * (tmcmc.py:908-962; uniform prior inside the box).  Nothing but the outputs crosses the PCIe bus.
+ * Parity with the reference is statistical: NumPy's PCG64 stream is not reproduced (the host-side mirror in
+ * tmcmc202601_b200/tmcmc.py keeps the bitwise stream).  The random numbers depend on (seed, sequence,
+ * index_offset + i, k) only, so a population sharded over several GPUs gets what one GPU would draw. */
+#define HMX_MUT_MAX_DIM 32
+typedef struct {
+    int32_t d;                          /* dimension of the particles (len(prior_bounds)), 1..HMX_MUT_MAX_DIM */
+    int32_t K;                          /* proposals per particle (n_mutation_steps after adaptation) */
+    double factor[HMX_MUT_MAX_DIM * HMX_MUT_MAX_DIM]; /* row-major [d,d]; factor factor^T = proposal covariance */
+    double low[HMX_MUT_MAX_DIM], high[HMX_MUT_MAX_DIM];
+    double theta_base[HMX_NTHETA];      /* theta_full starts from this ... */
+    int32_t map[HMX_MUT_MAX_DIM];       /* ... and theta_full[map[j]] = theta_sub[j], j < n_map (entries >= 20 are ignored) */
+    int32_t n_map;
+    double theta_lin[HMX_NTHETA];       /* np.allclose short-cut (tsm_analytical.py:366-401): a proposal within rtol 1e-5 /  */
+    int32_t cond_default, cond_at_lin;  /* atol 1e-8 of theta_lin is evaluated as condition cond_at_lin (< 0: short-cut off) */
+    double beta;                        /* beta_next of the stage */
+    uint64_t seed, sequence;            /* RNG key and per-call tag (stage / recovery attempt); sequence < 2^30 */
+    uint64_t index_offset;              /* global index of particle 0 of this call (sharded populations) */
+} hmx_mutation;
+
+typedef struct {
+    int64_t n_accepted, n_candidates;   /* accepted proposals / proposals inside the prior (tmcmc.py:952-960) */
+    int64_t n_nonfinite, n_maxiter, n_singular; /* status bits over the N K solves */
+} hmx_mutation_stats;
+
+/* theta_res[N,d], logL_res[N] -> theta_out[N,d], logL_out[N] (host or device pointers; in-place allowed).
+ * Optional outputs (may be NULL): props[N*K,d], logL_props[N*K] for diagnostics.  Synchronises the stream. */
+int hmx_mutate(hmx_ctx* ctx, const hmx_mutation* mut, const double* theta_res, const double* logL_res, int64_t N,
+               double* theta_out, double* logL_out, double* props, double* logL_props, hmx_mutation_stats* stats);
 
 #ifdef __cplusplus
 }

@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include "../../tmcmc202601_b200/csrc/hmx_obs.cuh"
+#include "../../tmcmc202601_b200/csrc/hmx_mutation.cuh"
 
 using namespace hmx;
 
@@ -126,6 +127,59 @@ int emu_rebase(const hmx_config* cfg, const double* theta, const double* x, cons
     DISPATCH(rebase_once, K, theta, x, g_old, Q_rebased, Q_direct, norms, finite);
     return 0;
 }
+
+// ---- device-side mutation (hmx_mutation.cuh) run serially on the host ------------------------------------------
+void emu_philox(const uint32_t* c, const uint32_t* k, uint32_t* out) {
+    const Philox4 p = philox4x32_10(c[0], c[1], c[2], c[3], k[0], k[1]);
+    for (int i = 0; i < 4; ++i) out[i] = p.v[i];
+}
+double emu_reflect(double x, double lo, double hi) { return reflect_into_bounds(x, lo, hi); }
+void emu_normals(uint64_t seed, uint32_t seq, uint64_t gidx, int n_pairs, double* z) {
+    MutationRng R = {(uint32_t)seed, (uint32_t)(seed >> 32), seq};
+    for (int j = 0; j < n_pairs; ++j) normal_pair(R, gidx, (uint32_t)j, z[2 * j], z[2 * j + 1]);
+}
+double emu_accept_uniform(uint64_t seed, uint32_t seq, uint64_t gidx) {
+    MutationRng R = {(uint32_t)seed, (uint32_t)(seed >> 32), seq};
+    return accept_uniform(R, gidx);
+}
+// phase 1 of hmx_mutate: proposals, full 20-vectors, condition ids, inside flags
+int emu_mutation_propose(const hmx_mutation* mut, const double* theta_res, long long N, double* props, double* theta_full,
+                         int32_t* cond_id, uint8_t* inside) {
+    MutationParams M;
+    make_mutation_params(*mut, M);
+    for (long long t = 0; t < N * M.K; ++t) {
+        const long long i = t / M.K;
+        double prop[kMutMaxDim], full[HMX_NTHETA];
+        const uint64_t gidx = (uint64_t)(M.index_offset * (unsigned long long)M.K) + (uint64_t)t;
+        const bool in = propose_one(M, theta_res + i * M.d, gidx, prop);
+        for (int j = 0; j < M.d; ++j) props[t * M.d + j] = prop[j];
+        cond_id[t] = expand_theta(M, prop, full);
+        for (int k = 0; k < HMX_NTHETA; ++k) theta_full[t * HMX_NTHETA + k] = full[k];
+        inside[t] = in ? 1 : 0;
+    }
+    return 0;
+}
+// phase 3: sequential accept / reject; counts[0] += accepted, counts[1] += candidates
+int emu_mutation_accept(const hmx_mutation* mut, const double* props, const double* ll, const uint8_t* inside, long long N,
+                        const double* theta_res, const double* logL_res, double* theta_out, double* logL_out, long long* counts) {
+    MutationParams M;
+    make_mutation_params(*mut, M);
+    for (long long i = 0; i < N; ++i) {
+        double cur[kMutMaxDim];
+        for (int j = 0; j < M.d; ++j) cur[j] = theta_res[i * M.d + j];
+        double cl = logL_res[i];
+        int acc = 0, cand = 0;
+        accept_chain(M, mut->beta, (uint64_t)(M.index_offset + (unsigned long long)i), props + (size_t)i * M.K * M.d, ll + i * M.K,
+                     inside + i * M.K, cur, cl, acc, cand);
+        for (int j = 0; j < M.d; ++j) theta_out[i * M.d + j] = cur[j];
+        logL_out[i] = cl;
+        counts[0] += acc;
+        counts[1] += cand;
+    }
+    return 0;
+}
+int emu_sizeof_mutation(void) { return (int)sizeof(hmx_mutation); }
+int emu_sizeof_mutation_stats(void) { return (int)sizeof(hmx_mutation_stats); }
 
 // struct layout checks for the ctypes mirror (tmcmc202601_b200/_abi.py)
 int emu_sizeof_config(void) { return (int)sizeof(hmx_config); }

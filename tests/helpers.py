@@ -62,6 +62,27 @@ class OracleEngine:
         logL, st, its, _ = orc.evaluate_hmx(self.config, theta, cond_id, n_threads=self.n_threads, details=True)
         return (logL, st.astype(np.uint32), its.astype(np.uint32)) if return_status else logL
 
+    def mutate(self, mutation, theta_res, logL_res, return_proposals=False):
+        """hmx_mutate with the kernels' own host-compiled arithmetic (tests/csrc/host_emu.cpp) around the oracle likelihood."""
+        emu = load_emu()
+        theta_res = np.ascontiguousarray(theta_res, dtype=np.float64)
+        logL_res = np.ascontiguousarray(logL_res, dtype=np.float64)
+        N, d = theta_res.shape
+        K = mutation.K
+        props = np.empty((N * K, d))
+        full = np.empty((N * K, 20))
+        cond = np.empty(N * K, dtype=np.int32)
+        inside = np.empty(N * K, dtype=np.uint8)
+        emu.emu_mutation_propose(C.byref(mutation), dptr(theta_res), C.c_longlong(N), dptr(props), dptr(full), dptr(cond), dptr(inside))
+        ll, st, _ = self.loglik_batch(full, cond, return_status=True)
+        theta_out, logL_out = np.empty_like(theta_res), np.empty_like(logL_res)
+        counts = np.zeros(2, dtype=np.int64)
+        emu.emu_mutation_accept(C.byref(mutation), dptr(props), dptr(np.ascontiguousarray(ll)), dptr(inside), C.c_longlong(N),
+                                dptr(theta_res), dptr(logL_res), dptr(theta_out), dptr(logL_out), dptr(counts))
+        stats = {"n_accepted": int(counts[0]), "n_candidates": int(counts[1]), "n_nonfinite": int(((st & 1) != 0).sum()),
+                 "n_maxiter": int(((st & 2) != 0).sum()), "n_singular": int(((st & 4) != 0).sum())}
+        return (theta_out, logL_out, stats, props, ll) if return_proposals else (theta_out, logL_out, stats)
+
     def weighted_moments(self, theta, w):
         return np.concatenate([[w.sum(), (w * w).sum()], (theta * w[:, None]).sum(axis=0)])
 

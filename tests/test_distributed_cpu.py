@@ -64,8 +64,30 @@ def _worker(rank, world, port, out_dir):
         ev = D.ShardedEvaluator(Ev())
         res = tmcmc.run_TMCMC(ev, [(-1.0, 1.0), (-1.0, 1.0), (0.0, 2.0)], n_particles=120, n_stages=30, seed=99,
                               min_delta_beta=0.02, max_delta_beta=0.5, n_mutation_steps=2, stage_ops=D.ShardedStageOps(Ops()))
+        # 4. sharded device-side mutation: every rank mutates its block with GLOBAL Philox counters
+        from tmcmc202601_b200 import workloads
+        from tmcmc202601_b200.evaluator import LogLikelihoodEvaluator
+
+        cd = workloads.load_conditions()["Dysbiotic_HOBIC"]
+        obs_rows = np.array([3, 6, 9, 12, 14])
+
+        def factory(cfg):
+            for o, v in enumerate(obs_rows):
+                cfg.cond[0].idx_sparse[o] = cfg.cond[1].idx_sparse[o] = int(v)
+            return OracleEngine(cfg, n_threads=1)
+
+        theta_base = np.array(cd["bounds"]).mean(axis=1)
+        inner = LogLikelihoodEvaluator(dict(workloads.PRODUCTION_SOLVER, maxtimestep=15, phi_init=cd["phi_init"]), [0, 1, 2, 3, 4],
+                                       list(range(20)), theta_base, cd["data"], obs_rows, cd["sigma_obs"], cov_rel=0.005,
+                                       engine_factory=factory)
+        b = np.array(cd["bounds"])
+        pop = np.random.default_rng(4).uniform(b[:, 0], b[:, 1], size=(21, 20))
+        ll0 = D.ShardedEvaluator(inner).batch(pop)
+        fac = np.diag(0.02 * (b[:, 1] - b[:, 0]))
+        th_m, ll_m, st_m = D.ShardedEvaluator(inner).mutate_device(pop, ll0, fac, b[:, 0], b[:, 1], 3, 0.3, seed=77, sequence=2)
         np.savez(Path(out_dir) / f"rank{rank}.npz", samples=res.samples, logL=res.logL_values, beta=np.array(res.beta_schedule),
-                 n_local=Ev.n_local)
+                 n_local=Ev.n_local, mut_theta=th_m, mut_logL=ll_m, mut_stats=np.array([st_m["n_accepted"], st_m["n_candidates"]]),
+                 pop=pop, ll0=ll0)
     finally:
         dist.destroy_process_group()
 
@@ -89,6 +111,30 @@ def test_world_size_2_gloo(tmp_path):
                            min_delta_beta=0.02, max_delta_beta=0.5, n_mutation_steps=2, stage_ops=OracleStageOps())
     assert np.allclose(solo.beta_schedule, r0["beta"], rtol=1e-12)
     assert np.allclose(solo.samples, r0["samples"], rtol=1e-9, atol=1e-12)
+
+    # device-side mutation: both ranks hold the same gathered result, and it is bitwise what ONE process produces
+    assert np.array_equal(r0["mut_theta"], r1["mut_theta"]) and np.array_equal(r0["mut_logL"], r1["mut_logL"])
+    assert np.array_equal(r0["mut_stats"], r1["mut_stats"]) and r0["mut_stats"][1] == 21 * 3
+    from helpers import OracleEngine
+    from tmcmc202601_b200 import workloads
+    from tmcmc202601_b200.evaluator import LogLikelihoodEvaluator
+
+    cd = workloads.load_conditions()["Dysbiotic_HOBIC"]
+    obs_rows = np.array([3, 6, 9, 12, 14])
+
+    def factory(cfg):
+        for o, v in enumerate(obs_rows):
+            cfg.cond[0].idx_sparse[o] = cfg.cond[1].idx_sparse[o] = int(v)
+        return OracleEngine(cfg)
+
+    b = np.array(cd["bounds"])
+    one = LogLikelihoodEvaluator(dict(workloads.PRODUCTION_SOLVER, maxtimestep=15, phi_init=cd["phi_init"]), [0, 1, 2, 3, 4],
+                                 list(range(20)), b.mean(axis=1), cd["data"], obs_rows, cd["sigma_obs"], cov_rel=0.005,
+                                 engine_factory=factory)
+    th1, ll1, st1 = one.mutate_device(r0["pop"], r0["ll0"], np.diag(0.02 * (b[:, 1] - b[:, 0])), b[:, 0], b[:, 1], 3, 0.3, seed=77, sequence=2)
+    assert np.array_equal(th1, r0["mut_theta"]) and np.array_equal(ll1, r0["mut_logL"])
+    assert [st1["n_accepted"], st1["n_candidates"]] == r0["mut_stats"].tolist()
+    assert 0 < st1["n_accepted"] <= 63  # (15 time steps: the likelihood is almost flat)
 
 
 def test_shard_bounds_partition():

@@ -70,12 +70,82 @@ class HmxCounters(C.Structure):
     ]
 
 
+MUT_MAX_DIM = 32
+
+
+class HmxMutation(C.Structure):
+    _fields_ = [
+        ("d", C.c_int32),
+        ("K", C.c_int32),
+        ("factor", C.c_double * (MUT_MAX_DIM * MUT_MAX_DIM)),
+        ("low", C.c_double * MUT_MAX_DIM),
+        ("high", C.c_double * MUT_MAX_DIM),
+        ("theta_base", C.c_double * NTHETA),
+        ("map", C.c_int32 * MUT_MAX_DIM),
+        ("n_map", C.c_int32),
+        ("theta_lin", C.c_double * NTHETA),
+        ("cond_default", C.c_int32),
+        ("cond_at_lin", C.c_int32),
+        ("beta", C.c_double),
+        ("seed", C.c_uint64),
+        ("sequence", C.c_uint64),
+        ("index_offset", C.c_uint64),
+    ]
+
+
+class HmxMutationStats(C.Structure):
+    _fields_ = [
+        ("n_accepted", C.c_int64),
+        ("n_candidates", C.c_int64),
+        ("n_nonfinite", C.c_int64),
+        ("n_maxiter", C.c_int64),
+        ("n_singular", C.c_int64),
+    ]
+
+
+def make_mutation(factor, lows, highs, K, beta, seed, sequence=0, index_offset=0, theta_base=None, active_map=None,
+                  theta_lin=None, cond_default=0, cond_at_lin=-1) -> HmxMutation:
+    """Fill an hmx_mutation.  `active_map[j]` is the position of theta_sub[j] in the 20-vector (default: identity);
+    entries >= 20 (the viscoelastic parameters) do not reach the ODE."""
+    factor = np.ascontiguousarray(factor, dtype=np.float64)
+    d = factor.shape[0]
+    if factor.shape != (d, d) or not 1 <= d <= MUT_MAX_DIM:
+        raise ValueError(f"factor must be square with 1 <= d <= {MUT_MAX_DIM}")
+    lows = np.asarray(lows, dtype=np.float64).reshape(-1)
+    highs = np.asarray(highs, dtype=np.float64).reshape(-1)
+    if lows.size != d or highs.size != d:
+        raise ValueError("bounds and factor disagree on the dimension")
+    m = HmxMutation()
+    m.d, m.K = d, int(K)
+    for i in range(d * d):
+        m.factor[i] = factor.flat[i]
+    for j in range(d):
+        m.low[j], m.high[j] = lows[j], highs[j]
+    base = np.zeros(NTHETA) if theta_base is None else np.asarray(theta_base, dtype=np.float64).reshape(-1)[:NTHETA]
+    amap = list(range(min(d, NTHETA))) if active_map is None else [int(a) for a in active_map][:d]
+    for k in range(NTHETA):
+        m.theta_base[k] = base[k] if k < base.size else 0.0
+    for j, a in enumerate(amap):
+        m.map[j] = a
+    m.n_map = len(amap)
+    lin = base if theta_lin is None else np.asarray(theta_lin, dtype=np.float64).reshape(-1)[:NTHETA]
+    for k in range(NTHETA):
+        m.theta_lin[k] = lin[k] if k < lin.size else 0.0
+    m.cond_default, m.cond_at_lin = int(cond_default), int(cond_at_lin)
+    m.beta = float(beta)
+    m.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    m.sequence = int(sequence)
+    m.index_offset = int(index_offset)
+    return m
+
+
 EXPORTS = [
     "hmx_create", "hmx_destroy", "hmx_last_error", "hmx_set_stream", "hmx_synchronize", "hmx_abi_version",
     "hmx_loglik_batch", "hmx_trajectory_batch", "hmx_beta_step", "hmx_weights", "hmx_resample",
     "hmx_weighted_cov", "hmx_weighted_moments", "hmx_weighted_scatter", "hmx_log_likelihood_sparse", "hmx_get_counters",
     "hmx_set_timing",
     "hmx_measure_fp64_peak",
+    "hmx_mutate",
 ]
 
 
@@ -217,6 +287,7 @@ def load() -> C.CDLL:
     lib.hmx_get_counters.argtypes = [vp, C.POINTER(HmxCounters)]
     lib.hmx_set_timing.argtypes = [vp, C.c_int32]
     lib.hmx_measure_fp64_peak.argtypes = [vp, dp]
+    lib.hmx_mutate.argtypes = [vp, C.POINTER(HmxMutation), vp, vp, C.c_int64, vp, vp, vp, vp, C.POINTER(HmxMutationStats)]
     del ip, up, lp
     if lib.hmx_abi_version() != ABI_VERSION:
         raise RuntimeError("libhamilton.so ABI version mismatch; rebuild")

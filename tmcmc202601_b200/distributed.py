@@ -42,26 +42,29 @@ def _comm_device(group=None):
     return torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
 
 
-def all_gather_blocks(local: np.ndarray, n_total: int, group=None) -> np.ndarray:
-    """All-gather of contiguous float64 blocks laid out by shard_bounds (blocks differ by at most one element)."""
+def all_gather_blocks(local: np.ndarray, n_total: int, group=None, unit: int = 1) -> np.ndarray:
+    """All-gather of contiguous float64 blocks laid out by shard_bounds (blocks differ by at most one row).
+    `unit` > 1: rows of `unit` elements (n_total counts elements, the split is by rows)."""
     import torch
 
     dist = _dist()
     G, r = dist.get_world_size(group), dist.get_rank(group)
-    width = -(-int(n_total) // G) if n_total else 0
+    unit = int(unit)
+    rows = int(n_total) // unit
+    width = (-(-rows // G) if rows else 0) * unit
     dev = _comm_device(group)
     send = torch.zeros(max(width, 1), dtype=torch.float64, device=dev)
-    lo, hi = shard_bounds(n_total, G, r)
-    assert local.shape[0] == hi - lo, "local block does not match shard_bounds"
+    lo, hi = shard_bounds(rows, G, r)
+    assert local.shape[0] == (hi - lo) * unit, "local block does not match shard_bounds"
     if hi > lo:
-        send[: hi - lo] = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64)).to(dev)
+        send[: (hi - lo) * unit] = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64)).to(dev)
     recv = torch.empty(G * max(width, 1), dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(recv, send, group=group)
     recv = recv.cpu().numpy().reshape(G, max(width, 1))
-    out = np.empty(int(n_total), dtype=np.float64)
+    out = np.empty(rows * unit, dtype=np.float64)
     for k in range(G):
-        a, b = shard_bounds(n_total, G, k)
-        out[a:b] = recv[k, : b - a]
+        a, b = shard_bounds(rows, G, k)
+        out[a * unit:b * unit] = recv[k, : (b - a) * unit]
     return out
 
 
@@ -99,6 +102,27 @@ class ShardedEvaluator:
         lo, hi = shard_bounds(n, G, r)
         local = self._inner.batch(theta[lo:hi]) if hi > lo else np.empty(0)
         return all_gather_blocks(np.asarray(local, dtype=np.float64), n, self._group)
+
+
+    def mutate_device(self, theta_res, logL_res, factor, lows, highs, K, beta_next, seed, sequence=0, index_offset=0):
+        """Device-side mutation of this rank's block; the Philox counters use the GLOBAL particle index, so the
+        gathered population is bitwise what a single GPU would produce."""
+        dist = _dist()
+        theta_res = np.ascontiguousarray(theta_res, dtype=np.float64)
+        logL_res = np.ascontiguousarray(logL_res, dtype=np.float64)
+        n, d = theta_res.shape
+        G, r = dist.get_world_size(self._group), dist.get_rank(self._group)
+        lo, hi = shard_bounds(n, G, r)
+        if hi > lo:
+            th, ll, st = self._inner.mutate_device(theta_res[lo:hi], logL_res[lo:hi], factor, lows, highs, K, beta_next, seed,
+                                                   sequence=sequence, index_offset=index_offset + lo)
+        else:
+            th, ll, st = np.empty((0, d)), np.empty(0), {}
+        keys = ["n_accepted", "n_candidates", "n_nonfinite", "n_maxiter", "n_singular"]
+        tot = all_reduce_sum(np.array([float(st.get(k, 0)) for k in keys]), self._group)
+        theta = all_gather_blocks(np.ascontiguousarray(th).reshape(-1), n * d, self._group, unit=d).reshape(n, d)
+        logL = all_gather_blocks(np.asarray(ll, dtype=np.float64), n, self._group)
+        return theta, logL, {k: int(v) for k, v in zip(keys, tot)}
 
 
 class ShardedStageOps:

@@ -116,6 +116,30 @@ class HamiltonEngine:
         self._check(self._lib.hmx_trajectory_batch(self._ctx, _addr(theta), _addr(cid), N, _addr(g), _addr(status), _addr(iters)), "hmx_trajectory_batch")
         return g, status, iters
 
+    # -- device-side mutation -------------------------------------------------------------
+    def mutate(self, mutation: "_abi.HmxMutation", theta_res, logL_res, return_proposals: bool = False):
+        """K Gaussian MH steps for every resampled particle, entirely on the device (hmx_mutate).
+
+        Returns (theta_new[N,d], logL_new[N], stats dict) and, with `return_proposals`, the N*K proposals and their
+        log-likelihoods."""
+        theta_res = np.ascontiguousarray(theta_res, dtype=np.float64)
+        logL_res = np.ascontiguousarray(logL_res, dtype=np.float64)
+        N, d = theta_res.shape
+        if d != mutation.d or logL_res.shape != (N,):
+            raise ValueError("theta_res must be (N, d) with d == mutation.d and logL_res (N,)")
+        theta_out, logL_out = np.empty_like(theta_res), np.empty_like(logL_res)
+        props = np.empty((N * mutation.K, d)) if return_proposals else None
+        llp = np.empty(N * mutation.K) if return_proposals else None
+        st = _abi.HmxMutationStats()
+        self._check(
+            self._lib.hmx_mutate(self._ctx, C.byref(mutation), _addr(theta_res), _addr(logL_res), N, _addr(theta_out), _addr(logL_out),
+                                 _addr(props), _addr(llp), C.byref(st)),
+            "hmx_mutate",
+        )
+        stats = {"n_accepted": st.n_accepted, "n_candidates": st.n_candidates, "n_nonfinite": st.n_nonfinite,
+                 "n_maxiter": st.n_maxiter, "n_singular": st.n_singular}
+        return (theta_out, logL_out, stats, props, llp) if return_proposals else (theta_out, logL_out, stats)
+
     # -- stage arithmetic -------------------------------------------------------------------------------
     def beta_step(self, logL, beta, target_ess_ratio=0.5, min_delta_beta=0.02, max_delta_beta=0.5):
         logL = logL if _is_torch(logL) else np.ascontiguousarray(logL, dtype=np.float64)

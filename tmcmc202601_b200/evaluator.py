@@ -217,6 +217,35 @@ class LogLikelihoodEvaluator:
     def __call__(self, theta_sub: np.ndarray) -> float:
         return float(self.batch(np.asarray(theta_sub, dtype=np.float64)[None, :], record_history=True)[0])
 
+    def mutation_map(self, d: int) -> List[int]:
+        """Position of theta_sub[j] in the full vector, exactly as _full_theta scatters it (-1: column unused)."""
+        if self.strict_mapping and d == self.theta_base.size:
+            act = set(int(i) for i in self.active_indices)
+            return [j if j in act else -1 for j in range(d)]
+        if len(self.active_indices) > d:
+            raise ValueError("theta_sub has fewer columns than active_indices")
+        return [int(i) for i in self.active_indices]
+
+    def mutate_device(self, theta_res: np.ndarray, logL_res: np.ndarray, factor: np.ndarray, lows, highs, K: int,
+                      beta_next: float, seed: int, sequence: int = 0, index_offset: int = 0):
+        """K-step MH mutation of the resampled population on the GPU (hmx_mutate; reference TM:849-962 with Philox
+        instead of PCG64).  Returns (theta[N,d], logL[N], stats)."""
+        if self.ve_prior is not None:
+            raise NotImplementedError("the viscoelastic prior is host-side arithmetic; use the host mutation path")
+        theta_res = np.ascontiguousarray(theta_res, dtype=np.float64)
+        N, d = theta_res.shape
+        mut = _abi.make_mutation(factor, lows, highs, K, beta_next, seed, sequence=sequence, index_offset=index_offset,
+                                 theta_base=self.theta_base[:_abi.NTHETA], active_map=self.mutation_map(d),
+                                 theta_lin=self._theta_linearization[:_abi.NTHETA], cond_default=0, cond_at_lin=1)
+        with timed(self.timing, "tsm.solve_tsm"):
+            theta, logL, st = self._engine.mutate(mut, theta_res, logL_res)
+        self.call_count += int(st["n_candidates"])
+        self.health.n_calls += N * int(K)
+        self.health.n_output_nonfinite += int(st["n_nonfinite"])
+        self.health.n_max_newton_iter += int(st["n_maxiter"])
+        self.health.n_singular_direction += int(st["n_singular"])
+        return theta, logL, st
+
     def close(self):
         self._engine.close()
 

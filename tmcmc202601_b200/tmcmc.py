@@ -284,9 +284,12 @@ def run_TMCMC(
     dreamzs_gamma: Optional[float] = None,
     dreamzs_snooker_prob: float = 0.1,
     stage_ops: Optional[Any] = None,
+    device_mutation: bool = False,
 ) -> TMCMCResult:
-    """One TMCMC chain (TM:393-1842).  Extra keyword `stage_ops` selects the stage-arithmetic backend
-    (default: the GPU)."""
+    """One TMCMC chain (TM:393-1842).  Extra keywords: `stage_ops` selects the stage-arithmetic backend (default:
+    the GPU); `device_mutation=True` runs proposal generation, reflection, likelihood and accept/reject of every
+    stage on the GPU (`log_likelihood.mutate_device`, Philox random numbers: same algorithm and constants, a
+    different random stream, so results agree with the host path statistically, not bitwise)."""
     _validate_tmcmc_inputs(log_likelihood, prior_bounds, n_particles, n_stages, target_ess_ratio, evaluator,
                            theta_base_full, active_indices)
     if proposal_type != "gaussian":
@@ -294,10 +297,20 @@ def run_TMCMC(
     if beta_schedule not in ("ess", "cov"):
         raise ValueError("beta_schedule must be 'ess' or 'cov'")
     ops = stage_ops or get_stage_ops(evaluator)
+    if device_mutation:
+        if not callable(getattr(log_likelihood, "mutate_device", None)):
+            raise ValueError("device_mutation=True needs a likelihood with .mutate_device (LogLikelihoodEvaluator)")
+        if gnn_prior is not None:
+            raise NotImplementedError("device_mutation supports the uniform box prior only")
     # CoV(w) <= c  <=>  ESS >= N / (1 + c^2): the "cov" schedule (TM:636-643) is the ESS bisection with this ratio
     ess_ratio = target_ess_ratio if beta_schedule == "ess" else 1.0 / (1.0 + float(target_cov) ** 2)
 
     rng = np.random.default_rng(seed)
+    # key of the device-side Philox stream: a function of `seed` only, drawn from a separate generator so that the
+    # host stream (initial population, resampling offsets, subset draws) is the same with and without device_mutation
+    mut_seed = int(np.random.default_rng([0x6D757461, int(seed) & 0xFFFFFFFF if seed is not None else 0]).integers(0, 2**63)) \
+        if seed is not None else int(np.random.default_rng().integers(0, 2**63))
+    mut_sequence = 0
     t_start = time.perf_counter()
     n_params = len(prior_bounds)
     lows = np.array([b[0] for b in prior_bounds], dtype=np.float64)
@@ -380,9 +393,17 @@ def run_TMCMC(
 
         def mutate(cov_matrix: np.ndarray, steps: int):
             """K-step mutation of the whole population (TM:849-962)."""
+            nonlocal mut_sequence
             K = int(max(1, steps))
             base_theta = theta_after_resample
             base_logL = logL_after_resample
+            if device_mutation:
+                th_new, ll_new, st = log_likelihood.mutate_device(base_theta, base_logL, _mvn_factor(cov_matrix), lows, highs, K,
+                                                                  beta_next, mut_seed, sequence=mut_sequence)
+                mut_sequence += 1
+                total = int(st["n_candidates"])
+                n_acc = int(st["n_accepted"])
+                return th_new, ll_new, (n_acc / total if total > 0 else 0.0), n_acc, total
             # proposals: mean + z @ (u sqrt(s))^T with z drawn exactly like N*K successive multivariate_normal calls
             factor = _mvn_factor(cov_matrix)
             z = rng.standard_normal((n_particles * K, n_params))
@@ -652,6 +673,7 @@ def run_multi_chain_TMCMC(
     use_threads: bool = False,
     gnn_prior: Optional[Any] = None,
     stage_ops: Optional[Any] = None,
+    device_mutation: bool = False,
 ):
     """Sequential chains with the reference's seeding and MAP hand-over (TM:2104-2381).
     Returns (all_samples, all_logL, global_MAP, converged_flags, diagnostics)."""
@@ -671,7 +693,7 @@ def run_multi_chain_TMCMC(
             update_linearization_interval=update_linearization_interval, n_mutation_steps=n_mutation_steps,
             use_observation_based_update=use_observation_based_update, linearization_threshold=linearization_threshold,
             linearization_enable_rom_threshold=linearization_enable_rom_threshold, force_beta_one=force_beta_one,
-            gnn_prior=gnn_prior, stage_ops=stage_ops,
+            gnn_prior=gnn_prior, stage_ops=stage_ops, device_mutation=device_mutation,
         )
         all_samples.append(res.samples)
         all_logL.append(res.logL_values)
