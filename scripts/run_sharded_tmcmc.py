@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--mutation-steps", type=int, default=5)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--n-hill", type=float, default=4.0)
+    ap.add_argument("--device-mutation", action="store_true", help="proposals / accept-reject on the GPU (Philox stream)")
+    ap.add_argument("--tag", default="")
     args = ap.parse_args()
 
     import torch
@@ -57,14 +59,15 @@ def main():
         t0 = time.perf_counter()
         res = tmcmc.run_TMCMC(like, bounds, n_particles=args.particles, n_stages=30, seed=4242, min_delta_beta=0.02, max_delta_beta=0.5,
                               evaluator=like, theta_base_full=base, active_indices=cd["active_indices"],
-                              n_mutation_steps=args.mutation_steps, stage_ops=sops)
+                              n_mutation_steps=args.mutation_steps, stage_ops=sops, device_mutation=args.device_mutation)
         wall = time.perf_counter() - t0
         n_local = ev.health.n_calls
         ev.close()
         return res, wall, n_local
 
     res, wall, n_local = run(world > 1)
-    out = {"world": world, "particles": args.particles, "condition": args.condition, "n_hill": args.n_hill, "wall_s": wall,
+    out = {"world": world, "particles": args.particles, "condition": args.condition, "n_hill": args.n_hill, "device_mutation": bool(args.device_mutation), "wall_s": wall,
+           "likelihood_wall_s": res.timing_breakdown_s["tsm_s"] if res.timing_breakdown_s else None,
            "stages": len(res.stage_summary), "beta": res.beta_schedule[-1], "local_evaluations": int(n_local),
            "logL_max": float(res.logL_values.max()), "log_evidence": res.log_evidence,
            "acc": [round(a, 3) for a in res.acc_rate_history]}
@@ -88,7 +91,7 @@ def main():
     if rank == 0:
         print(json.dumps(out), flush=True)
         (ROOT / "gpurun_out").mkdir(exist_ok=True)
-        (ROOT / "gpurun_out" / f"sharded_tmcmc_w{world}.json").write_text(json.dumps(out, indent=1))
+        (ROOT / "gpurun_out" / f"sharded_tmcmc_w{world}{args.tag}.json").write_text(json.dumps(out, indent=1))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
