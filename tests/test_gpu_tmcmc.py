@@ -84,3 +84,41 @@ def test_merged_four_condition_run_equals_sequential(built):
     assert np.array_equal(np.concatenate(out[k]["chains"], axis=0), samples)
     assert np.array_equal(np.concatenate(out[k]["logL"]), ll)
     print(summary)
+
+
+def test_estimate_writes_a_reference_shaped_run_directory(built, tmp_path):
+    """SURVEY 8(f)2 on the device: `rundir.estimate` end to end (device-side mutation), and fit_metrics.json at the
+    stored reference MAP / mean equal to the reference's own file (trajectories from hmx_trajectory_batch)."""
+    import json
+
+    from tmcmc202601_b200 import rundir
+
+    res = rundir.estimate("Dysbiotic_HOBIC_legacy_1k30", tmp_path / "run", n_particles=400, n_chains=2, device_mutation=True)
+    out = tmp_path / "run"
+    schema = json.loads((GOLDEN / "rundir_schema.json").read_text())
+    have = {p.name for p in out.iterdir()}
+    assert set(schema["_files"]) - {"figures", "figures_pub", "diagnostics_tables", "log_tmcmc.txt"} <= have
+    assert np.load(out / "samples.npy").shape == (800, 20) and all(res["converged"])
+    fm = json.loads((out / "fit_metrics.json").read_text())
+    assert set(schema["fit_metrics.json"]) <= set(fm) and set(schema["fit_metrics.json"]["MAP"]) <= set(fm["MAP"])
+    assert fm["MAP"]["n_obs"] == 6 and fm["MAP"]["rmse_total"] < 0.5
+
+    g = np.load(GOLDEN / "rundir_dh_1k30.npz")
+    cd = workloads.load_conditions()["Dysbiotic_HOBIC_legacy_1k30"]
+    ref = rundir.fit_metrics_for(g["theta_MAP_full"], g["theta_mean_full"], dict(workloads.PRODUCTION_SOLVER, phi_init=0.02), cd["data"],
+                                 cd["idx_sparse"])
+    # the reference builds this file with a solver WITHOUT the Hill gate (MAIN:3452-3459): reproduced by default
+    from oracle import oracle as orc
+    from tmcmc202601_b200 import posterior
+
+    ocfg = orc.make_solver_cfg(phi_init=0.02, **dict(workloads.PRODUCTION_SOLVER, K_hill=0.0, n_hill=2.0))
+    for k, th in (("MAP", g["theta_MAP_full"]), ("Mean", g["theta_mean_full"])):
+        _, go, *_ = orc.run_deterministic(ocfg, th)
+        want = posterior.compute_fit_metrics(None, go, [0, 1, 2, 3, 4], cd["data"], cd["idx_sparse"])
+        for m in ("rmse_per_species", "mae_per_species", "rmse_total", "mae_total", "max_abs"):
+            assert np.allclose(ref[k][m], want[m], rtol=1e-9, atol=0), (k, m)
+            # the stored file was written by an older revision of the reference solver: same quirk, 1e-5-level drift
+            assert np.allclose(ref[k][m], g[f"fit_{k}_{m}"], rtol=2e-4, atol=0), (k, m)
+    gated = rundir.fit_metrics_for(g["theta_MAP_full"], g["theta_mean_full"], dict(workloads.PRODUCTION_SOLVER, phi_init=0.02), cd["data"],
+                                   cd["idx_sparse"], with_hill_gate=True)
+    assert gated["MAP"]["rmse_total"] < 0.6 * ref["MAP"]["rmse_total"]  # the calibrated model fits far better than the plotted one
