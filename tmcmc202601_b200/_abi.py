@@ -145,7 +145,7 @@ EXPORTS = [
     "hmx_weighted_cov", "hmx_weighted_moments", "hmx_weighted_scatter", "hmx_log_likelihood_sparse", "hmx_get_counters",
     "hmx_set_timing",
     "hmx_measure_fp64_peak",
-    "hmx_mutate",
+    "hmx_mutate", "hmx_trajectory_rows",
 ]
 
 
@@ -277,6 +277,7 @@ def load() -> C.CDLL:
     # array arguments are raw addresses (host or device), hence c_void_p everywhere
     lib.hmx_loglik_batch.argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp, vp]
     lib.hmx_trajectory_batch.argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp]
+    lib.hmx_trajectory_rows.argtypes = [vp, vp, vp, C.c_int64, vp, C.c_int32, vp, vp, vp]
     lib.hmx_beta_step.argtypes = [vp, vp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp]
     lib.hmx_weights.argtypes = [vp, vp, C.c_int64, C.c_double, vp, vp]
     lib.hmx_resample.argtypes = [vp, vp, C.c_int64, C.c_double, vp]

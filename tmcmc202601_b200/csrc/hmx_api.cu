@@ -71,6 +71,10 @@ struct hmx_ctx {
     long long last_evals = 0;
     long long chunk_evals = kDefaultChunkEvals;  // HMX_CHUNK_EVALS overrides (tests exercise the multi-chunk path with it)
     long long launches = 0;
+    // row selection of the trajectory call in flight (hmx_trajectory_rows); null = all n_steps + 1 levels
+    const int32_t* cur_row_map = nullptr;
+    int cur_n_rows = 0;
+    DevBuf row_map;
 };
 
 namespace {
@@ -217,6 +221,8 @@ int run_chunk(hmx_ctx* ctx, const double* d_theta, const int32_t* d_cond, long l
     P.pairs = (double*)ctx->pairs.p;
     P.pair_stride = pair_stride;
     P.traj = d_traj;
+    P.traj_row_map = ctx->cur_row_map;
+    P.traj_n_rows = ctx->cur_row_map ? ctx->cur_n_rows : ctx->cfg.n_steps + 1;
     P.status = d_status;
     P.iters = d_iters;
     P.trips = (uint32_t*)ctx->trips.p;
@@ -287,10 +293,12 @@ int batch_impl(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, long l
     CU(cudaMemsetAsync(ctx->d_counters + 1, 0, 2 * sizeof(unsigned long long), ctx->stream));
     if (N == 0) return 0;
     const long long obs_stride = (long long)std::max(ctx->n_obs_max, 1) * 12;
-    const long long traj_stride = (long long)(ctx->cfg.n_steps + 1) * 12;
+    const long long traj_stride = (long long)(ctx->cur_row_map ? ctx->cur_n_rows : ctx->cfg.n_steps + 1) * 12;
+    // trajectories are 100-240 KB per evaluation: keep a chunk's output below ~8 GiB
+    const long long chunk = traj ? std::max(1ll, std::min(ctx->chunk_evals, (8ll << 30) / (traj_stride * 8))) : ctx->chunk_evals;
     bool need_sync = false;
-    for (long long off = 0; off < N; off += ctx->chunk_evals) {
-        const long long n = std::min(ctx->chunk_evals, N - off);
+    for (long long off = 0; off < N; off += chunk) {
+        const long long n = std::min(chunk, N - off);
         int rc;
         const void *d_theta, *d_cond;
         void *d_logL, *d_obs, *d_status, *d_iters, *d_traj;
@@ -315,7 +323,7 @@ int batch_impl(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, long l
         const bool any_host = h_logL || h_obs || h_status || h_iters || h_traj;
         need_sync = need_sync || any_host;
         // staging buffers are reused by the next chunk: drain before overwriting them
-        if (off + ctx->chunk_evals < N && (any_host || !is_device_ptr(theta))) CU(cudaStreamSynchronize(ctx->stream));
+        if (off + chunk < N && (any_host || !is_device_ptr(theta))) CU(cudaStreamSynchronize(ctx->stream));
     }
     if (need_sync) CU(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -406,7 +414,7 @@ void hmx_destroy(hmx_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->theta, &ctx->cond_id, &ctx->pairs, &ctx->status, &ctx->iters, &ctx->trips, &ctx->logL,
                       &ctx->obs_state, &ctx->traj, &ctx->st_in0, &ctx->st_in1, &ctx->st_in2, &ctx->st_out0, &ctx->st_out1,
                       &ctx->partial, &ctx->cs, &ctx->order, &ctx->m_props, &ctx->m_theta, &ctx->m_cond, &ctx->m_inside,
-                      &ctx->m_ll, &ctx->m_status, &ctx->m_in_theta, &ctx->m_in_logL, &ctx->m_out_theta, &ctx->m_out_logL};
+                      &ctx->m_ll, &ctx->m_status, &ctx->m_in_theta, &ctx->m_in_logL, &ctx->m_out_theta, &ctx->m_out_logL, &ctx->row_map};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->d_cond) cudaFree(ctx->d_cond);
@@ -445,6 +453,33 @@ int hmx_trajectory_batch(hmx_ctx* ctx, const double* theta, const int32_t* cond_
     if (!ctx) return HMX_ERR_INVALID;
     if (!g && N > 0) return fail(ctx, HMX_ERR_INVALID, "g is NULL");
     return batch_impl(ctx, theta, cond_id, N, nullptr, nullptr, status, newton_iters, g);
+}
+
+int hmx_trajectory_rows(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, int64_t N, const int32_t* rows, int32_t n_rows,
+                        double* g, uint32_t* status, uint32_t* newton_iters) {
+    if (!ctx) return HMX_ERR_INVALID;
+    if (!g && N > 0) return fail(ctx, HMX_ERR_INVALID, "g is NULL");
+    const int T = ctx->cfg.n_steps;
+    if (!rows || n_rows < 1 || n_rows > T + 1) return fail(ctx, HMX_ERR_INVALID, "hmx_trajectory_rows: need 1 <= n_rows <= n_steps + 1");
+    std::string map((size_t)(T + 1) * sizeof(int32_t), '\0');
+    int32_t* m = (int32_t*)&map[0];
+    for (int t = 0; t <= T; ++t) m[t] = -1;
+    for (int r = 0; r < n_rows; ++r) {
+        if (rows[r] < 0 || rows[r] > T || (r > 0 && rows[r] <= rows[r - 1]))
+            return fail(ctx, HMX_ERR_INVALID, "hmx_trajectory_rows: rows must be strictly ascending in [0, n_steps]");
+        m[rows[r]] = r;
+    }
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure(ctx, ctx->row_map, map.size());
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->row_map.p, m, map.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // `map` lives on this stack frame
+    ctx->cur_row_map = (const int32_t*)ctx->row_map.p;
+    ctx->cur_n_rows = n_rows;
+    rc = batch_impl(ctx, theta, cond_id, N, nullptr, nullptr, status, newton_iters, g);
+    ctx->cur_row_map = nullptr;
+    ctx->cur_n_rows = 0;
+    return rc;
 }
 
 int hmx_beta_step(hmx_ctx* ctx, const double* logL, int64_t N, double beta, double target_ess_ratio,

@@ -51,7 +51,9 @@ struct OdeParams {
     long long N;
     double* pairs;           // [N, n_obs_max, 24]
     long long pair_stride;   // n_obs_max * 24
-    double* traj;            // [N, n_steps+1, 12] or null
+    double* traj;            // [N, n_steps+1, 12] (or [N, traj_n_rows, 12] with a row map) or null
+    const int32_t* traj_row_map;  // [n_steps+1]: output row of time level t, -1 = not stored; null = every level
+    int traj_n_rows;
     uint32_t* status;        // [N]
     uint32_t* iters;         // [N]
     uint32_t* trips;         // [N]
@@ -111,9 +113,12 @@ __global__ void HMX_ODE_BOUNDS ode_kernel(const __grid_constant__ OdeParams P) {
             for (int k = 0; k < HMX_NTHETA; ++k) th[k] = __ldg(tp + k);
             lane_init(P.K, s, th, P.cond[c].g0);
             if (P.traj) {
-                double* tr = P.traj + w * (long long)(P.K.n_steps + 1) * 12;
+                const int r0 = P.traj_row_map ? P.traj_row_map[0] : 0;
+                if (r0 >= 0) {
+                    double* tr = P.traj + (w * (long long)P.traj_n_rows + r0) * 12;
 #pragma unroll
-                for (int i = 0; i < 12; ++i) tr[i] = s.g[i];
+                    for (int i = 0; i < 12; ++i) tr[i] = s.g[i];
+                }
             }
             next_obs = 0;
             next_t = (P.cond[c].n_obs > 0) ? max(P.cond[c].idx[0], 1) : 0x7fffffff;
@@ -137,9 +142,12 @@ __global__ void HMX_ODE_BOUNDS ode_kernel(const __grid_constant__ OdeParams P) {
                 } while (step_idx + 1 == next_t);
             }
             if (P.traj) {
-                double* q = P.traj + w * (long long)(P.K.n_steps + 1) * 12 + (long long)(step_idx + 1) * 12;
+                const int r = P.traj_row_map ? P.traj_row_map[step_idx + 1] : step_idx + 1;
+                if (r >= 0) {
+                    double* q = P.traj + (w * (long long)P.traj_n_rows + r) * 12;
 #pragma unroll
-                for (int i = 0; i < 12; ++i) q[i] = g[i];
+                    for (int i = 0; i < 12; ++i) q[i] = g[i];
+                }
             }
         };
         if (lane_trip<ALPHA, HILL>(P.K, s, step_end)) {

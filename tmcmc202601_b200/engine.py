@@ -116,6 +116,19 @@ class HamiltonEngine:
         self._check(self._lib.hmx_trajectory_batch(self._ctx, _addr(theta), _addr(cid), N, _addr(g), _addr(status), _addr(iters)), "hmx_trajectory_batch")
         return g, status, iters
 
+    def trajectory_rows(self, theta, rows, cond_id=None):
+        """g[N, len(rows), 12]: the time levels `rows` (strictly ascending) of every trajectory (hmx_trajectory_rows)."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        N = theta.shape[0]
+        rows = np.ascontiguousarray(rows, dtype=np.int32).reshape(-1)
+        cid = None if cond_id is None else np.ascontiguousarray(cond_id, dtype=np.int32)
+        g = np.empty((N, rows.size, _abi.NSTATE))
+        status = np.zeros(N, dtype=np.uint32)
+        iters = np.zeros(N, dtype=np.uint32)
+        self._check(self._lib.hmx_trajectory_rows(self._ctx, _addr(theta), _addr(cid), N, _addr(rows), rows.size, _addr(g), _addr(status),
+                                                  _addr(iters)), "hmx_trajectory_rows")
+        return g, status, iters
+
     # -- device-side mutation (SURVEY 8(f)1) -------------------------------------------------------------
     def mutate(self, mutation: "_abi.HmxMutation", theta_res, logL_res, return_proposals: bool = False):
         """K Gaussian MH steps for every resampled particle, entirely on the device (hmx_mutate).

@@ -68,16 +68,23 @@ class BiofilmNewtonSolver5S:
             b[i] = theta[k]
         return A, b
 
-    def run_deterministic_batch(self, theta):
-        theta = np.ascontiguousarray(np.atleast_2d(np.real(theta)), dtype=np.float64)
-        g, _, _ = self._eng().trajectory_batch(theta[:, :20])
-        return g
-
-    def run_deterministic(self, theta):
-        g = self.run_deterministic_batch(np.asarray(theta, dtype=np.float64)[None, :])[0]
+    def time_array(self) -> np.ndarray:
         t_arr = np.empty(self.maxtimestep + 1)
         t_arr[0] = 0.0
         t_arr[1:] = (np.arange(self.maxtimestep) + 1) * self.dt  # tt = (step + 1) * dt, S5:860
-        return t_arr, g
+        return t_arr
+
+    def run_deterministic_batch(self, theta, rows=None, return_status=False):
+        """g[N, T+1, 12] for theta[N, 20]; with `rows` (ascending time levels) only g[N, len(rows), 12] leaves the GPU."""
+        theta = np.ascontiguousarray(np.atleast_2d(np.real(theta)), dtype=np.float64)
+        if rows is None:
+            g, st, _ = self._eng().trajectory_batch(theta[:, :20])
+        else:
+            g, st, _ = self._eng().trajectory_rows(theta[:, :20], rows)
+        return (g, st) if return_status else g
+
+    def run_deterministic(self, theta):
+        g = self.run_deterministic_batch(np.asarray(theta, dtype=np.float64)[None, :])[0]
+        return self.time_array(), g
 
     solve = run_deterministic  # alias used by the TSM wrapper (S5:646)
