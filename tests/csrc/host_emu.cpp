@@ -199,7 +199,7 @@ double emu_solve5x2(const double* M, double* X, int pivoted) {
     double S[5][7];
     for (int r = 0; r < 5; ++r)
         for (int c = 0; c < 7; ++c) S[r][c] = M[r * 7 + c];
-    const double pmin = (pivoted == 2) ? solve5x2_block23(S) : solve5x2_natural(S);
+    const double pmin = (pivoted == 2) ? solve5x2_block23(S) : (solve5x2_natural(S) ? 1.0 : 0.0);
     for (int r = 0; r < 5; ++r) {
         X[r] = S[r][5];
         X[5 + r] = S[r][6];

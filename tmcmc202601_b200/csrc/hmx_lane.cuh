@@ -208,9 +208,16 @@ HMX_HD bool lane_trip(const SolverConsts& K, Lane& s, StepEnd&& step_end) {
         } else {
             s.step *= 0.5;
             if (!(s.step > 1e-4)) {
-                // no improving step length: full step, keep the old norm
+                // no improving step length: full step, keep the old norm.  This is also where a non-finite
+                // direction ends up (every trial along it has a non-finite residual and is rejected), so the
+                // finiteness test of the direction lives here, off the hot path.
+                double chk = 0.0;
 #pragma unroll
-                for (int i = 0; i < 12; ++i) s.g[i] = s.g[i] + s.d[i];
+                for (int i = 0; i < 12; ++i) {
+                    chk = fma(s.d[i], 0.0, chk);
+                    s.g[i] = s.g[i] + s.d[i];
+                }
+                if (chk != 0.0) s.status |= kStSingular;
                 if (s.normQ < s.tol || s.it >= K.max_iter) {
                     finished = true;
                 } else {
@@ -274,10 +281,6 @@ HMX_HD bool lane_trip(const SolverConsts& K, Lane& s, StepEnd&& step_end) {
     HMX_WARP_CONVERGE();
     if (need_dir) {
         direction<ALPHA, HILL>(K, e, s.A, s.b, s.d, s.stash);
-        double chk = 0.0;
-#pragma unroll
-        for (int i = 0; i < 12; ++i) chk = fma(s.d[i], 0.0, chk);
-        if (chk != 0.0) s.status |= kStSingular;  // inf/NaN direction
         ++s.it;
         ++s.iters;
         s.step = 1.0;

@@ -247,17 +247,17 @@ HMX_HD void residual(const SolverConsts& K, const double (&x)[12], const GPT& gp
 //
 // The matrix is S = I + diag(g) C with g_i = q_i^T D_i^{-1} p_i ~ dt and |C_ij| = c/eta |A_ij|, i.e. a small
 // perturbation of the identity for every physically meaningful input (|g C| ~ 0.07 at the production MAP).
-// Fast path: elimination in natural order, fully unrolled, registers only.  It reports the smallest pivot
-// magnitude; when that drops below kPivotFloor the caller redoes the solve with partial pivoting
+// Fast path: elimination in natural order, fully unrolled, registers only.  It reports whether every pivot
+// magnitude stayed above kPivotFloor; when not, the caller redoes the solve with partial pivoting
 // (solve5x2_pivoted, local memory, dynamic indexing -- off the hot path).
 constexpr double kPivotFloor = 0.0625;
 
-HMX_HD double solve5x2_natural(double (&S)[5][7]) {
+HMX_HD bool solve5x2_natural(double (&S)[5][7]) {
     double rp[5];
-    double pmin = 1e300;
+    bool ok = true;  // every pivot at least kPivotFloor in magnitude (a NaN pivot fails the test)
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-        pmin = fmin(pmin, fabs(S[k][k]));
+        ok = ok && (fabs(S[k][k]) >= kPivotFloor);
         rp[k] = rcp(S[k][k]);
 #pragma unroll
         for (int r = k + 1; r < 5; ++r) {
@@ -277,7 +277,7 @@ HMX_HD double solve5x2_natural(double (&S)[5][7]) {
         S[k][5] = s0 * rp[k];
         S[k][6] = s1 * rp[k];
     }
-    return pmin;  // NaN-safe: fmin ignores NaN pivots, the caller also checks the direction for finiteness
+    return ok;
 }
 
 // Same system by 2+3 block elimination: explicit 2x2 inverse, Schur complement, 3x3 adjugate.  Only two
@@ -432,11 +432,11 @@ HMX_HD void direction(const SolverConsts& K, const Eval& e, const AT& A, const d
         S[i][6] = fma(u, b0, v * b1);
     }
 #if defined(HMX_SOLVE_BLOCK23)
-    const double health = solve5x2_block23(S);  // shorter dependency chain, a few more live values; measured 2 % slower
+    const bool healthy = solve5x2_block23(S) >= kPivotFloor;  // shorter dependency chain, a few more live values; measured 2 % slower
 #else
-    const double health = solve5x2_natural(S);
+    const bool healthy = solve5x2_natural(S);
 #endif
-    if (!(health >= kPivotFloor)) {  // rare: rebuild the system and redo it with row pivoting
+    if (!healthy) {  // rare: rebuild the system and redo it with row pivoting
         double T[5][7], X[10];
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
