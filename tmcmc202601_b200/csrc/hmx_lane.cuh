@@ -176,9 +176,12 @@ template <bool ALPHA, int HILL, class StepEnd>
 HMX_HD bool lane_trip(const SolverConsts& K, Lane& s, StepEnd&& step_end) {
     double x[12];
     const bool trial = (s.mode == kModeTrial);
+    // candidate = g + step d in a trial, g itself at an iteration start: one fma with step := 0 instead of a
+    // select per component (0 * d + g == g exactly because d is finite whenever the mode is "iteration start":
+    // it is zeroed at lane_init and after a non-finite direction, see below)
     const double sl = trial ? s.step : 0.0;
 #pragma unroll
-    for (int i = 0; i < 12; ++i) x[i] = trial ? fma(sl, s.d[i], s.g[i]) : s.g[i];
+    for (int i = 0; i < 12; ++i) x[i] = fma(sl, s.d[i], s.g[i]);
 
     Eval e;
     residual<ALPHA, HILL>(K, x, s.gp, s.A, s.b, e);
@@ -217,7 +220,11 @@ HMX_HD bool lane_trip(const SolverConsts& K, Lane& s, StepEnd&& step_end) {
                     chk = fma(s.d[i], 0.0, chk);
                     s.g[i] = s.g[i] + s.d[i];
                 }
-                if (chk != 0.0) s.status |= kStSingular;
+                if (chk != 0.0) {
+                    s.status |= kStSingular;
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) s.d[i] = 0.0;
+                }
                 if (s.normQ < s.tol || s.it >= K.max_iter) {
                     finished = true;
                 } else {
