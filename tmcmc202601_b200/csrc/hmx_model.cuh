@@ -164,10 +164,27 @@ template <bool ALPHA, int HILL, class GPT, class AT>
 HMX_HD void residual(const SolverConsts& K, const double (&x)[12], const GPT& gp,
                      const AT& A, const double (&b)[5], Eval& e) {
     const double gam = x[11];
+    // phi, psi inside the box is the overwhelmingly common case: one ordered compare pair per value and a
+    // branch around the selects (NaN fails the test and takes the clip path, which leaves it NaN like S5:66-69)
+#if defined(HMX_CLIP_BRANCH)
+    bool inbox = true;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        e.ph[i] = clip01(x[i]);
-        e.ps[i] = clip01(x[6 + i]);
+    for (int i = 0; i < 5; ++i)
+        inbox = inbox && (x[i] >= kClipLo) && (x[i] <= kClipHi) && (x[6 + i] >= kClipLo) && (x[6 + i] <= kClipHi);
+    if (inbox) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            e.ph[i] = x[i];
+            e.ps[i] = x[6 + i];
+        }
+    } else
+#endif
+    {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            e.ph[i] = clip01(x[i]);
+            e.ps[i] = clip01(x[6 + i]);
+        }
     }
     const double ph0 = clip01(x[5]);
     const double m2K = -2.0 * K.Kp1;
