@@ -231,3 +231,18 @@ def test_parity_distribution_over_prior_draws(engines):
     assert rel.max() < REL
     assert np.quantile(rel, 0.999) < 1e-10
     assert np.array_equal(st & 1, rst & 1)
+
+
+def test_active_species_masks_against_live_reference_trajectories(built):
+    """BiofilmNewtonSolver5S(active_species=..., phi_init=vector) on the device vs the live reference solver."""
+    from tmcmc202601_b200.solver import BiofilmNewtonSolver5S
+
+    k = np.load(GOLDEN / "solver_masked_kat.npz")
+    for name in ("four_species", "three_species_vec", "all_vec"):
+        s = BiofilmNewtonSolver5S(dt=1e-4, maxtimestep=400, c_const=25.0, alpha_const=0.0, Kp1=1e-4, K_hill=0.05, n_hill=4.0,
+                                  phi_init=k[f"{name}_phi_init"], active_species=list(k[f"{name}_active"]))
+        t, g = s.run_deterministic(k[f"{name}_theta"])
+        ref = k[f"{name}_g"]
+        assert np.array_equal(g[0], ref[0])
+        rel = np.abs(g - ref) / np.maximum(np.abs(ref), 1e-300)
+        assert rel.max() < 1e-9, (name, rel.max())

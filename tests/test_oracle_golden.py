@@ -166,3 +166,17 @@ def test_nonfinite_theta_gives_sentinel():
     th[0] = np.nan  # ... a11 is not
     ll, obs, st, its, tr = orc.evaluate(cfg, cc, th, want_obs=True)
     assert ll == -1e20 and (st & orc.ST_NONFINITE)
+
+
+def test_active_species_masks_and_vector_phi_init_against_live_reference():
+    """Solver variants outside the main fixture set (tests/golden/make_golden_masked.py): inactive species start at
+    phi = psi = 0 and are held at the clip floor by the barrier (S5:563-575)."""
+    k = np.load(GOLDEN / "solver_masked_kat.npz")
+    for name in ("four_species", "three_species_vec", "all_vec"):
+        cfg = orc.make_solver_cfg(phi_init=k[f"{name}_phi_init"], active_species=list(k[f"{name}_active"]), dt=1e-4, maxtimestep=400,
+                                  c_const=25.0, alpha_const=0.0, Kp1=1e-4, K_hill=0.05, n_hill=4.0)
+        _, g, *_ = orc.run_deterministic(cfg, k[f"{name}_theta"])
+        ref = k[f"{name}_g"]
+        assert np.array_equal(g[0], ref[0])
+        rel = np.abs(g - ref) / np.maximum(np.abs(ref), 1e-300)
+        assert rel.max() < 1e-9, (name, rel.max())

@@ -220,3 +220,23 @@ def test_config_validation():
     bad3 = _abi.make_config([workloads.cond_struct(cd)], **workloads.PRODUCTION_SOLVER)
     bad3.abi_version = 99
     assert emu.emu_validate(C.byref(bad3)) != 0
+
+
+def test_active_species_masks_against_live_reference_trajectories():
+    """The lane state machine with inactive species (phi = psi = 0 at t = 0, held at the clip floor) and a vector
+    phi_init, against trajectories of the live reference solver (tests/golden/solver_masked_kat.npz)."""
+    from helpers import GOLDEN
+
+    k = np.load(GOLDEN / "solver_masked_kat.npz")
+    for name in ("four_species", "three_species_vec", "all_vec"):
+        hc = _abi.make_cond(np.zeros((1, 5)), [400], 1.0, k[f"{name}_phi_init"], tsm_variance=False)
+        cfg = _abi.make_config([hc], dt=1e-4, maxtimestep=400, c_const=25.0, alpha_const=0.0, Kp1=1e-4, K_hill=0.05, n_hill=4.0,
+                               active_species=list(k[f"{name}_active"]))
+        g = np.zeros((401, 12))
+        ll, st, it, tr = C.c_double(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        th = np.ascontiguousarray(k[f"{name}_theta"])
+        assert emu.emu_evaluate(C.byref(cfg), 0, dptr(th), dptr(g), C.byref(ll), C.byref(st), C.byref(it), C.byref(tr)) == 0
+        ref = k[f"{name}_g"]
+        assert np.array_equal(g[0], ref[0])
+        rel = np.abs(g - ref) / np.maximum(np.abs(ref), 1e-300)
+        assert rel.max() < 1e-9, (name, rel.max())

@@ -26,11 +26,9 @@ class BiofilmNewtonSolver5S:
     def __init__(self, dt=1e-5, maxtimestep=500, eps=1e-6, Kp1=1e-4, eta_vec=None, eta_phi_vec=None,
                  c_const=100.0, alpha_const=100.0, alpha_schedule=None, phi_init=0.2, active_species=None,
                  use_numba=True, max_newton_iter=50, K_hill=0.0, n_hill=2.0, device=0):
-        if alpha_schedule is not None:
-            raise NotImplementedError("alpha_schedule belongs to the legacy 4-species pipeline (SURVEY 8(f)-4)")
         self.dt, self.maxtimestep, self.eps, self.Kp1 = float(dt), int(maxtimestep), float(eps), float(Kp1)
         self.c_const, self.alpha_const = float(c_const), float(alpha_const)
-        self.alpha_schedule = None
+        self.alpha_schedule = alpha_schedule  # stored and never read by the 5-species reference solver either (S5:474, 488)
         self.phi_init = _abi.broadcast_phi_init(phi_init)
         self.max_newton_iter = int(max_newton_iter)
         self.K_hill, self.n_hill = float(K_hill), float(n_hill)
