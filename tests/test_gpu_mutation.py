@@ -106,3 +106,27 @@ def test_production_run_with_device_mutation_matches_reference_posterior(built):
     assert 0.75 < cmp_["std_ratio_min"] and cmp_["std_ratio_max"] < 1.33
     assert cmp_["quantile_shift_over_std_max"] < 0.5
     assert abs(out["logL_max"] - cmp_["logL_max_ref"]) < 1.5 and abs(out["logL_mean"] - cmp_["logL_mean_ref"]) < 0.5
+
+
+def test_hmx_mutate_and_trajectory_rows_across_chunks(built, monkeypatch):
+    """N K proposals above the chunk size go through the ODE kernel in pieces; the result must not depend on it."""
+    cfg, mut, theta_res, b = _setup(N=64, off=0)
+    eng = HamiltonEngine(cfg, 0)
+    logL_res = eng.loglik_batch(theta_res, np.zeros(64, dtype=np.int32))
+    whole = eng.mutate(mut, theta_res, logL_res, return_proposals=True)
+    rows = np.array([0, 7, 1200, 2500])
+    g0, _, _ = eng.trajectory_rows(theta_res, rows)
+    eng.close()
+    monkeypatch.setenv("HMX_CHUNK_EVALS", "50")
+    eng2 = HamiltonEngine(cfg, 0)
+    try:
+        parts = eng2.mutate(mut, theta_res, logL_res, return_proposals=True)
+        g1, _, _ = eng2.trajectory_rows(theta_res, rows)
+    finally:
+        eng2.close()
+    for a, c in zip(whole, parts):
+        if isinstance(a, dict):
+            assert a == c
+        else:
+            assert np.array_equal(a, c)
+    assert np.array_equal(g0, g1)
