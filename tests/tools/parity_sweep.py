@@ -1,7 +1,7 @@
 """Parity distribution of the GPU log-likelihoods against the CPU oracle over many prior draws
 ("check 1e-9 parity on 10^4 theta from each condition's prior").
 
-    python scripts/parity_sweep.py [n_per_condition=10000] [out=gpurun_out/parity_sweep.json]
+    python tests/tools/parity_sweep.py [n_per_condition=10000] [out=gpurun_out/parity_sweep.json]
 """
 import json
 import sys
@@ -10,7 +10,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 from oracle import oracle as orc  # noqa: E402  (checker)
 from tmcmc202601_b200 import workloads  # noqa: E402
