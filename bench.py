@@ -22,6 +22,9 @@ A "step" is one pass of the hot path over one batch:
 `roofline`: FP64 FMA pipe (the path is compute bound; HBM traffic is ~1.2 KB per 2e7-flop evaluation).
 `cpu_baseline` / `--impl reference`: the oracle's C restatement of the reference algorithm (kind "port": the
            reference itself is Python+numba and its tree does not travel to the GPU box) on all host threads.
+`tmcmc_run`: (N = 1, after the timed regions) the other half of BASELINE.json's metric, "TMCMC wall time per run": configs[1]
+           through the reference-shaped API, host-side and device-side mutation, posterior checked against the stored
+           reference run (226 865 s there).  --no-tmcmc-run skips it.
 """
 
 from __future__ import annotations
@@ -186,12 +189,35 @@ def workload_config(n_gpus: int, per_step_note: str = "") -> dict:
     }
 
 
+def tmcmc_run():
+    """Second half of BASELINE.json's metric ("TMCMC wall time per run"), outside the timed region: configs[1], the stored
+    production run (Dysbiotic HOBIC, K_hill=0.05, n_hill=4, N=1000 particles x 2 chains, seed 42), through the
+    reference-shaped API -- once with the host-side mutation loop (NumPy stream of the reference) and once with the
+    device-side mutation (hmx_mutate) -- with the posterior checked against the reference run's own samples."""
+    sys.path.insert(0, str(ROOT / "scripts"))
+    import run_production_tmcmc as rp
+
+    out = {"config": "BASELINE.json configs[1]: Dysbiotic HOBIC production run, N=1000 x 2 chains, K=0.05 n=4, seed 42",
+           "reference_wall_s": 226864.8}
+    for key, dev in (("host_mutation", False), ("device_mutation", True)):
+        try:
+            res, samples, ll = rp.run_condition("Dysbiotic_HOBIC_legacy_1k30", 1000, 2, device_mutation=dev)
+            cmp_ = rp.compare_with_reference(samples, ll)
+            out[key] = {"wall_s": res["wall_s"], "likelihood_evaluations": res["likelihood_evaluations"], "stages": res["stages"],
+                        "converged": res["converged"], "posterior_z_mean_max": cmp_["z_mean_max"],
+                        "posterior_std_ratio": [cmp_["std_ratio_min"], cmp_["std_ratio_max"]], "logL_max": res["logL_max"]}
+        except Exception as e:  # the throughput line must not be lost to a failure of the side measurement
+            out[key] = {"error": f"{type(e).__name__}: {e}"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-tmcmc-run", action="store_true", help="skip the configs[1] TMCMC wall-time side measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -349,7 +375,8 @@ def main():
     ode_avg_ms = float(np.mean(ode_ms))
     flops_per_launch = (FLOPS_PER_RESIDUAL * trips_sum + FLOPS_PER_DIRECTION * iters_sum) / args.steps
     achieved = flops_per_launch / (ode_avg_ms * 1e-3) / 1e12
-    ref_equiv = ((REF_FLOPS_PER_ITER * iters_sum + REF_FLOPS_PER_TRIAL * max(trips_sum - iters_sum - 2500 * M * args.steps, 0)) / args.steps
+    # rejected line-search trials = residual evaluations that were not followed by a direction (step starts are rebased, not evaluated)
+    ref_equiv = ((REF_FLOPS_PER_ITER * iters_sum + REF_FLOPS_PER_TRIAL * max(trips_sum - iters_sum, 0)) / args.steps
                  / (ode_avg_ms * 1e-3) / 1e12)
     roofline = {
         "bound": "fp64", "kernel": "hmx::ode_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
@@ -375,6 +402,8 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl)
+        if world == 1 and not args.no_tmcmc_run:
+            line["tmcmc_run"] = tmcmc_run()
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
