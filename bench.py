@@ -388,6 +388,10 @@ def main():
         "flops_per_launch": flops_per_launch, "newton_iters_per_eval": iters_sum / (M * args.steps),
         "residual_evals_per_eval": trips_sum / (M * args.steps),
         "reference_equivalent_tflops": ref_equiv,
+        # SURVEY 8(d)'s ALGORITHMIC count (dense Jacobian + LU: 2778 flop per iteration, 384 per extra trial) over the same
+        # kernel time: what the reference's formulation would have to sustain for this evaluation rate.  `achieved` / `frac`
+        # above count the flops this kernel actually executes (block-structured solve), which is the smaller number.
+        "algorithmic_frac_of_peak": ref_equiv / fp64_peak if fp64_peak > 0 else None,
         "hbm_algorithmic_bytes_per_eval": 20 * 8 + 4 + 5 * 24 * 8 + 12 + 8,
     }
 
