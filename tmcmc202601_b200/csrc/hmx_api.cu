@@ -461,6 +461,7 @@ int hmx_trajectory_rows(hmx_ctx* ctx, const double* theta, const int32_t* cond_i
     if (!g && N > 0) return fail(ctx, HMX_ERR_INVALID, "g is NULL");
     const int T = ctx->cfg.n_steps;
     if (!rows || n_rows < 1 || n_rows > T + 1) return fail(ctx, HMX_ERR_INVALID, "hmx_trajectory_rows: need 1 <= n_rows <= n_steps + 1");
+    if (is_device_ptr(rows)) return fail(ctx, HMX_ERR_INVALID, "hmx_trajectory_rows: rows must be a host array");
     std::string map((size_t)(T + 1) * sizeof(int32_t), '\0');
     int32_t* m = (int32_t*)&map[0];
     for (int t = 0; t <= T; ++t) m[t] = -1;
