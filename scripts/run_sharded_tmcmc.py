@@ -56,6 +56,10 @@ def main():
                                     cov_rel=0.005, theta_linearization=base, device=local)
         ops = tmcmc.GpuStageOps(engine=ev._engine)
         like, sops = (D.ShardedEvaluator(ev), D.ShardedStageOps(ops)) if sharded else (ev, ops)
+        if sharded:  # communicator set-up (channels, peer connections) belongs to process start-up, not to the run
+            D.all_gather_blocks(np.zeros(D.shard_bounds(world * 4, world, rank)[1] - D.shard_bounds(world * 4, world, rank)[0]), world * 4)
+            D.all_reduce_sum(np.zeros(8))
+            dist.barrier()
         t0 = time.perf_counter()
         res = tmcmc.run_TMCMC(like, bounds, n_particles=args.particles, n_stages=30, seed=4242, min_delta_beta=0.02, max_delta_beta=0.5,
                               evaluator=like, theta_base_full=base, active_indices=cd["active_indices"],
