@@ -179,6 +179,7 @@ int hmx_measure_fp64_peak(hmx_ctx* ctx, double* tflops);
  * tmcmc202601_b200/tmcmc.py keeps the bitwise stream).  The random numbers depend on (seed, sequence,
  * index_offset + i, k) only, so a population sharded over several GPUs gets what one GPU would draw. */
 #define HMX_MUT_MAX_DIM 32
+#define HMX_MUT_MAX_GROUPS 64
 typedef struct {
     int32_t d;                          /* dimension of the particles (len(prior_bounds)), 1..HMX_MUT_MAX_DIM */
     int32_t K;                          /* proposals per particle (n_mutation_steps after adaptation) */
@@ -203,6 +204,14 @@ typedef struct {
  * Optional outputs (may be NULL): props[N*K,d], logL_props[N*K] for diagnostics.  Synchronises the stream. */
 int hmx_mutate(hmx_ctx* ctx, const hmx_mutation* mut, const double* theta_res, const double* logL_res, int64_t N,
                double* theta_out, double* logL_out, double* props, double* logL_props, hmx_mutation_stats* stats);
+
+/* Several independent populations (the chains and conditions of the reference's `--batch all`, estimate_reduced_nishioka.py:
+ * 1100-1267) in ONE set of launches: group g owns n_particles[g] consecutive rows of theta_res / logL_res and is mutated with
+ * muts[g] (own covariance factor, bounds, K, beta, seed, condition ids); all groups share d.  Equal, bit for bit, to calling
+ * hmx_mutate once per group; stats[n_groups].  Optional props / logL_props are group-major [sum_g n_g K_g, d]. */
+int hmx_mutate_groups(hmx_ctx* ctx, int32_t n_groups, const hmx_mutation* muts, const int64_t* n_particles, const double* theta_res,
+                      const double* logL_res, double* theta_out, double* logL_out, double* props, double* logL_props,
+                      hmx_mutation_stats* stats);
 
 #ifdef __cplusplus
 }

@@ -83,6 +83,9 @@ class OracleEngine:
                  "n_maxiter": int(((st & 2) != 0).sum()), "n_singular": int(((st & 4) != 0).sum())}
         return (theta_out, logL_out, stats, props, ll) if return_proposals else (theta_out, logL_out, stats)
 
+    def mutate_groups(self, mutations, theta_list, logL_list):
+        return [self.mutate(m, t, l) for m, t, l in zip(mutations, theta_list, logL_list)]
+
     def weighted_moments(self, theta, w):
         return np.concatenate([[w.sum(), (w * w).sum()], (theta * w[:, None]).sum(axis=0)])
 

@@ -56,3 +56,25 @@ def test_broker_survives_uneven_chain_lengths():
     out, stats = batch.run_batch_TMCMC(jobs, SOLVER, n_particles=16, n_stages=3, n_chains=3, seed=3, n_mutation_steps=1,
                                        stage_ops=OracleStageOps(), engine_factory=lambda cfg: OracleEngine(cfg, n_threads=4))
     assert len(out[0]["chains"]) == 3 and all(c.shape == (16, 20) for c in out[0]["chains"])
+
+
+def test_merged_device_mutation_equals_independent_chains():
+    """device_mutation=True through the broker: the chains' mutation steps are merged into mutate_groups calls, and every
+    chain still equals the same chain run on its own (the Philox counters do not depend on the grouping)."""
+    jobs = _jobs()
+    out, stats = batch.run_batch_TMCMC(jobs, SOLVER, n_particles=24, n_stages=4, n_chains=2, seed=7, n_mutation_steps=2,
+                                       stage_ops=OracleStageOps(), engine_factory=lambda cfg: OracleEngine(cfg, n_threads=4),
+                                       device_mutation=True)
+    assert stats["merged_launches"] >= 2 and stats["likelihood_evaluations"] > 4 * 24
+    for k, j in enumerate(jobs):
+        for chain in range(2):
+            ev = LogLikelihoodEvaluator(dict(SOLVER, phi_init=j["phi_init"]), [0, 1, 2, 3, 4], list(j["active_indices"]), j["theta_base"],
+                                        j["data"], j["idx_sparse"], j["sigma_obs"], cov_rel=0.005, theta_linearization=j["theta_base"],
+                                        engine_factory=lambda cfg: OracleEngine(cfg, n_threads=4))
+            s = (7 + tmcmc._stable_hash_int(j["model_tag"]) % (2**31) + 2 * 1000 + chain) % (2**31)
+            solo = tmcmc.run_TMCMC(ev, [tuple(b) for b in j["prior_bounds"]], n_particles=24, n_stages=4, seed=s, min_delta_beta=0.02,
+                                   max_delta_beta=0.5, evaluator=ev, theta_base_full=j["theta_base"], active_indices=list(j["active_indices"]),
+                                   n_mutation_steps=2, stage_ops=OracleStageOps(), device_mutation=True)
+            assert np.array_equal(solo.samples, out[k]["chains"][chain])
+            assert np.array_equal(solo.logL_values, out[k]["logL"][chain])
+            assert solo.acc_rate_history == out[k]["results"][chain].acc_rate_history

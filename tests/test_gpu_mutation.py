@@ -130,3 +130,42 @@ def test_hmx_mutate_and_trajectory_rows_across_chunks(built, monkeypatch):
         else:
             assert np.array_equal(a, c)
     assert np.array_equal(g0, g1)
+
+
+def test_mutate_groups_equals_separate_calls(built):
+    """hmx_mutate_groups: three populations (different covariance factor, K, beta, seed, condition slot, size) in one
+    set of launches == three hmx_mutate calls, bit for bit."""
+    cfg, mut, theta_res, b = _setup(N=80, off=0)
+    eng = HamiltonEngine(cfg, 0)
+    logL_res = eng.loglik_batch(theta_res, np.zeros(80, dtype=np.int32))
+    rng = np.random.default_rng(3)
+    specs = [(0, 30, 3, 0.6, 21, 0), (30, 31, 5, 0.25, 99, 1), (61, 80, 1, 1.0, 7, 0)]
+    muts, ths, lls = [], [], []
+    for lo, hi, K, beta, seed, cond in specs:
+        a = rng.normal(size=(20, 20)) * 0.03
+        m = _abi.make_mutation(tmcmc._mvn_factor(a @ a.T + 1e-6 * np.eye(20)), b[:, 0], b[:, 1], K, beta, seed, sequence=4, index_offset=lo,
+                               theta_base=b.mean(axis=1), active_map=list(range(20)), theta_lin=b.mean(axis=1), cond_default=cond, cond_at_lin=-1)
+        muts.append(m)
+        ths.append(theta_res[lo:hi])
+        lls.append(logL_res[lo:hi])
+    merged = eng.mutate_groups(muts, ths, lls)
+    for m, t, l, got in zip(muts, ths, lls, merged):
+        want = eng.mutate(m, t, l)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and got[2] == want[2]
+    assert merged[1][0].shape == (1, 20) and merged[2][2]["n_candidates"] == 19
+    eng.close()
+
+
+def test_merged_four_condition_run_with_device_mutation(built):
+    """BASELINE.json configs[2] with every stage on the device: four conditions x 2 chains, likelihood AND mutation launches
+    merged across the eight chains; each chain equals the same chain run alone with device-side mutation."""
+    sys.path.insert(0, str(GOLDEN.parents[1] / "scripts"))
+    import run_production_tmcmc as rp
+
+    summary, out = rp.run_merged(workloads.CONDITION_KEYS, 200, 2, device_mutation=True)
+    assert all(all(o["converged"]) for o in out) and summary["merged_launches"] < 40
+    solo, samples, ll = rp.run_condition("Commensal_HOBIC", 200, 2, device_mutation=True)
+    k = workloads.CONDITION_KEYS.index("Commensal_HOBIC")
+    assert np.array_equal(np.concatenate(out[k]["chains"], axis=0), samples)
+    assert np.array_equal(np.concatenate(out[k]["logL"]), ll)
+    print(summary)

@@ -39,18 +39,39 @@ class MergedLikelihoodBroker:
 
     def _flush_locked(self):
         reqs, self.pending = self.pending, []
-        theta = np.concatenate([r["theta"] for r in reqs], axis=0)
-        cid = np.concatenate([r["cond_id"] for r in reqs])
-        t0 = time.perf_counter()
+        mut = [r for r in reqs if r["kind"] == "mutate"]
+        ev = [r for r in reqs if r["kind"] == "loglik"]
         try:
-            with self.engine_lock:
-                logL, status, iters = self.engine.loglik_batch(theta, cid, return_status=True)
+            if mut:
+                self._launch_mutations(mut)
+            if ev:
+                self._launch_logliks(ev)
         except BaseException as e:  # wake everybody up with the error instead of dead-locking
             self.error = e
             for r in reqs:
                 r["done"] = True
             self.cv.notify_all()
             raise
+        self.cv.notify_all()
+
+    def _launch_mutations(self, reqs):
+        """All chains that reached their mutation step this round: ONE hmx_mutate_groups call (one ODE launch)."""
+        t0 = time.perf_counter()
+        with self.engine_lock:
+            res = self.engine.mutate_groups([r["mutation"] for r in reqs], [r["theta"] for r in reqs], [r["logL"] for r in reqs])
+        self.gpu_seconds += time.perf_counter() - t0
+        self.launches += 1
+        for r, out in zip(reqs, res):
+            self.evaluations += r["theta"].shape[0] * r["mutation"].K
+            r["result"] = out
+            r["done"] = True
+
+    def _launch_logliks(self, reqs):
+        theta = np.concatenate([r["theta"] for r in reqs], axis=0)
+        cid = np.concatenate([r["cond_id"] for r in reqs])
+        t0 = time.perf_counter()
+        with self.engine_lock:
+            logL, status, iters = self.engine.loglik_batch(theta, cid, return_status=True)
         self.gpu_seconds += time.perf_counter() - t0
         self.launches += 1
         self.evaluations += theta.shape[0]
@@ -60,10 +81,14 @@ class MergedLikelihoodBroker:
             r["result"] = (logL[off:off + n].copy(), status[off:off + n].copy(), iters[off:off + n].copy())
             r["done"] = True
             off += n
-        self.cv.notify_all()
 
     def submit(self, theta: np.ndarray, cond_id: np.ndarray):
-        req = {"theta": theta, "cond_id": cond_id, "done": False, "result": None}
+        return self._submit({"kind": "loglik", "theta": theta, "cond_id": cond_id, "done": False, "result": None})
+
+    def submit_mutation(self, mutation, theta_res: np.ndarray, logL_res: np.ndarray):
+        return self._submit({"kind": "mutate", "mutation": mutation, "theta": theta_res, "logL": logL_res, "done": False, "result": None})
+
+    def _submit(self, req):
         with self.cv:
             self.pending.append(req)
             if len(self.pending) >= self.active:
@@ -95,6 +120,15 @@ class _BrokerEngine:
         logL, status, iters = self.broker.submit(theta, (2 * self.slot + local).astype(np.int32))
         return (logL, status, iters) if return_status else logL
 
+    def mutate(self, mutation, theta_res, logL_res, return_proposals=False):
+        if return_proposals:
+            raise NotImplementedError("proposals are not returned through the merged path")
+        mutation.cond_default = 2 * self.slot + (mutation.cond_default & 1)
+        if mutation.cond_at_lin >= 0:
+            mutation.cond_at_lin = 2 * self.slot + (mutation.cond_at_lin & 1)
+        return self.broker.submit_mutation(mutation, np.ascontiguousarray(theta_res, dtype=np.float64),
+                                           np.ascontiguousarray(logL_res, dtype=np.float64))
+
     def close(self):
         pass
 
@@ -124,12 +158,13 @@ class _LockedStageOps:
 
 def run_batch_TMCMC(jobs: Sequence[Dict[str, Any]], solver_kwargs: Dict[str, Any], n_particles: int = 1000, n_stages: int = 30,
                     n_chains: int = 2, seed: int = 42, n_mutation_steps: int = 5, min_delta_beta: float = 0.02,
-                    max_delta_beta: float = 0.5, device: int = 0, stage_ops=None, engine_factory=None):
+                    max_delta_beta: float = 0.5, device: int = 0, stage_ops=None, engine_factory=None, device_mutation: bool = False):
     """Run len(jobs) x n_chains TMCMC chains concurrently on one GPU.
 
     jobs[k] needs: model_tag, data, idx_sparse, sigma_obs, phi_init, prior_bounds, theta_base, active_indices
     (optional: cov_rel=0.005, weights, use_absolute_volume).  All jobs share `solver_kwargs` (without phi_init).
     Returns one dict per job with the same five entries run_multi_chain_TMCMC returns, plus broker statistics.
+    `device_mutation=True`: the chains' mutation steps are merged as well (hmx_mutate_groups: one group per chain).
     """
     if not 1 <= len(jobs) <= _abi.MAX_COND // 2:
         raise ValueError(f"between 1 and {_abi.MAX_COND // 2} jobs per GPU context")
@@ -162,7 +197,7 @@ def run_batch_TMCMC(jobs: Sequence[Dict[str, Any]], solver_kwargs: Dict[str, Any
                 log_likelihood=ev, prior_bounds=[tuple(b) for b in j["prior_bounds"]], n_particles=n_particles, n_stages=n_stages,
                 min_delta_beta=min_delta_beta, max_delta_beta=max_delta_beta, seed=chain_seed,
                 model_name=f"{j['model_tag']}_chain{chain + 1}", evaluator=ev, theta_base_full=np.asarray(j["theta_base"], float),
-                active_indices=list(j["active_indices"]), n_mutation_steps=n_mutation_steps, stage_ops=ops)
+                active_indices=list(j["active_indices"]), n_mutation_steps=n_mutation_steps, stage_ops=ops, device_mutation=device_mutation)
         except BaseException as e:  # noqa: BLE001 - reported to the caller after all threads stopped
             errors.append(e)
         finally:

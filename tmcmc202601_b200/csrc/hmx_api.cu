@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/hmx.h"
 #include "hmx_consts.h"
@@ -55,7 +56,7 @@ struct hmx_ctx {
     // device scratch
     DevBuf theta, cond_id, pairs, status, iters, trips, logL, obs_state, traj;
     DevBuf st_in0, st_in1, st_in2, st_out0, st_out1, partial, cs, order;
-    DevBuf m_props, m_theta, m_cond, m_inside, m_ll, m_status, m_in_theta, m_in_logL, m_out_theta, m_out_logL;  // hmx_mutate
+    DevBuf m_props, m_theta, m_cond, m_inside, m_ll, m_status, m_in_theta, m_in_logL, m_out_theta, m_out_logL, m_groups;  // hmx_mutate
     unsigned long long* d_mut_counts = nullptr;  // [8] accepted, candidates, nonfinite, maxiter, singular
     SchedState* d_sched = nullptr;
     CondConsts* d_cond = nullptr;
@@ -394,7 +395,7 @@ int hmx_create(hmx_ctx** out, const hmx_config* cfg, int32_t device) {
     CU_CREATE(cudaMemset(ctx->d_stage, 0, sizeof(StageState)));
     CU_CREATE(cudaMalloc((void**)&ctx->d_tickets, 64 * sizeof(unsigned int)));
     CU_CREATE(cudaMemset(ctx->d_tickets, 0, 64 * sizeof(unsigned int)));
-    CU_CREATE(cudaMalloc((void**)&ctx->d_mut_counts, 8 * sizeof(unsigned long long)));
+    CU_CREATE(cudaMalloc((void**)&ctx->d_mut_counts, 8 * kMutMaxGroups * sizeof(unsigned long long)));
     CU_CREATE(cudaMalloc((void**)&ctx->d_small, 4096 * sizeof(double)));
     CU_CREATE(cudaEventCreate(&ctx->ev0));
     CU_CREATE(cudaEventCreate(&ctx->ev1));
@@ -414,7 +415,7 @@ void hmx_destroy(hmx_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->theta, &ctx->cond_id, &ctx->pairs, &ctx->status, &ctx->iters, &ctx->trips, &ctx->logL,
                       &ctx->obs_state, &ctx->traj, &ctx->st_in0, &ctx->st_in1, &ctx->st_in2, &ctx->st_out0, &ctx->st_out1,
                       &ctx->partial, &ctx->cs, &ctx->order, &ctx->m_props, &ctx->m_theta, &ctx->m_cond, &ctx->m_inside,
-                      &ctx->m_ll, &ctx->m_status, &ctx->m_in_theta, &ctx->m_in_logL, &ctx->m_out_theta, &ctx->m_out_logL, &ctx->row_map};
+                      &ctx->m_ll, &ctx->m_status, &ctx->m_in_theta, &ctx->m_in_logL, &ctx->m_out_theta, &ctx->m_out_logL, &ctx->row_map, &ctx->m_groups};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->d_cond) cudaFree(ctx->d_cond);
@@ -701,30 +702,41 @@ int hmx_log_likelihood_sparse(hmx_ctx* ctx, const double* mu, const double* sig,
     return HMX_OK;
 }
 
-int hmx_mutate(hmx_ctx* ctx, const hmx_mutation* mut, const double* theta_res, const double* logL_res, int64_t N,
-               double* theta_out, double* logL_out, double* props, double* logL_props, hmx_mutation_stats* stats) {
+int hmx_mutate_groups(hmx_ctx* ctx, int32_t n_groups, const hmx_mutation* muts, const int64_t* n_particles, const double* theta_res,
+                      const double* logL_res, double* theta_out, double* logL_out, double* props, double* logL_props,
+                      hmx_mutation_stats* stats) {
     if (!ctx) return HMX_ERR_INVALID;
-    if (!mut || !theta_res || !logL_res || !theta_out || !logL_out || N < 0)
-        return fail(ctx, HMX_ERR_INVALID, "hmx_mutate: NULL argument or N < 0");
-    if (mut->d < 1 || mut->d > HMX_MUT_MAX_DIM || mut->K < 1 || mut->n_map < 0 || mut->n_map > mut->d)
-        return fail(ctx, HMX_ERR_INVALID, "hmx_mutate: need 1 <= d <= 32, K >= 1, 0 <= n_map <= d");
-    if (mut->cond_default < 0 || mut->cond_default >= ctx->cfg.n_cond || mut->cond_at_lin >= ctx->cfg.n_cond)
-        return fail(ctx, HMX_ERR_INVALID, "hmx_mutate: condition id outside [0, n_cond)");
-    if (mut->sequence >= (1ull << 30)) return fail(ctx, HMX_ERR_INVALID, "hmx_mutate: sequence must be < 2^30");
-    static_assert(HMX_MUT_MAX_DIM == kMutMaxDim, "header and kernel disagree on the maximum dimension");
+    if (n_groups < 1 || n_groups > kMutMaxGroups || !muts || !n_particles || !theta_res || !logL_res || !theta_out || !logL_out)
+        return fail(ctx, HMX_ERR_INVALID, "hmx_mutate_groups: NULL argument or n_groups outside [1, 64]");
+    static_assert(HMX_MUT_MAX_DIM == kMutMaxDim && HMX_MUT_MAX_GROUPS == kMutMaxGroups, "header and kernel disagree");
+    const int d = muts[0].d;
+    long long N = 0, NK = 0;
+    std::vector<MutationGroup> host(n_groups);
+    for (int g = 0; g < n_groups; ++g) {
+        const hmx_mutation& m = muts[g];
+        if (m.d < 1 || m.d > HMX_MUT_MAX_DIM || m.K < 1 || m.n_map < 0 || m.n_map > m.d || n_particles[g] < 0)
+            return fail(ctx, HMX_ERR_INVALID, "hmx_mutate: need 1 <= d <= 32, K >= 1, 0 <= n_map <= d, N >= 0");
+        if (m.d != d) return fail(ctx, HMX_ERR_INVALID, "hmx_mutate_groups: all groups must share the particle dimension d");
+        if (m.cond_default < 0 || m.cond_default >= ctx->cfg.n_cond || m.cond_at_lin >= ctx->cfg.n_cond)
+            return fail(ctx, HMX_ERR_INVALID, "hmx_mutate: condition id outside [0, n_cond)");
+        if (m.sequence >= (1ull << 30)) return fail(ctx, HMX_ERR_INVALID, "hmx_mutate: sequence must be < 2^30");
+        make_mutation_params(m, host[g].M);
+        host[g].beta = m.beta;
+        host[g].part0 = N;
+        host[g].n_part = n_particles[g];
+        host[g].prop0 = NK;
+        N += n_particles[g];
+        NK += (long long)n_particles[g] * m.K;
+    }
     CU(cudaSetDevice(ctx->device));
-    if (stats) memset(stats, 0, sizeof(*stats));
+    if (stats) memset(stats, 0, sizeof(*stats) * n_groups);
     if (N == 0) return HMX_OK;
-    const int d = mut->d, K = mut->K;
-    const long long NK = (long long)N * K;
-
-    MutationParams M;
-    make_mutation_params(*mut, M);
 
     int rc;
     const void *d_res, *d_lres;
     if ((rc = stage_in(ctx, theta_res, (size_t)N * d * sizeof(double), ctx->m_in_theta, &d_res))) return rc;
     if ((rc = stage_in(ctx, logL_res, (size_t)N * sizeof(double), ctx->m_in_logL, &d_lres))) return rc;
+    if ((rc = ensure(ctx, ctx->m_groups, host.size() * sizeof(MutationGroup)))) return rc;
     if ((rc = ensure(ctx, ctx->m_props, (size_t)NK * d * sizeof(double)))) return rc;
     if ((rc = ensure(ctx, ctx->m_theta, (size_t)NK * HMX_NTHETA * sizeof(double)))) return rc;
     if ((rc = ensure(ctx, ctx->m_cond, (size_t)NK * sizeof(int32_t)))) return rc;
@@ -734,22 +746,25 @@ int hmx_mutate(hmx_ctx* ctx, const hmx_mutation* mut, const double* theta_res, c
     void *d_tout, *d_lout, *h_tout, *h_lout;
     if ((rc = stage_out(ctx, theta_out, (size_t)N * d * sizeof(double), ctx->m_out_theta, &d_tout, &h_tout))) return rc;
     if ((rc = stage_out(ctx, logL_out, (size_t)N * sizeof(double), ctx->m_out_logL, &d_lout, &h_lout))) return rc;
+    CU(cudaMemcpyAsync(ctx->m_groups.p, host.data(), host.size() * sizeof(MutationGroup), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // `host` is pageable and dies with this frame
+    const MutationGroup* d_groups = (const MutationGroup*)ctx->m_groups.p;
 
     const int threads = 128;
     const int grid_p = (int)std::min<long long>((NK + threads - 1) / threads, (long long)ctx->sm_count * 16);
-    propose_kernel<<<grid_p, threads, 0, ctx->stream>>>(M, (const double*)d_res, (long long)N, (double*)ctx->m_props.p,
+    propose_kernel<<<grid_p, threads, 0, ctx->stream>>>(d_groups, n_groups, (const double*)d_res, NK, (double*)ctx->m_props.p,
                                                         (double*)ctx->m_theta.p, (int32_t*)ctx->m_cond.p, (uint8_t*)ctx->m_inside.p);
     CU(cudaGetLastError());
     ctx->launches += 1;
-    // K1 + K1c on the N K proposals, device-resident (same code path as hmx_loglik_batch)
+    // K1 + K1c on all proposals of all groups in ONE launch, device-resident (same code path as hmx_loglik_batch)
     if ((rc = batch_impl(ctx, (const double*)ctx->m_theta.p, (const int32_t*)ctx->m_cond.p, NK, (double*)ctx->m_ll.p, nullptr,
                          (uint32_t*)ctx->m_status.p, nullptr, nullptr))) return rc;
-    CU(cudaMemsetAsync(ctx->d_mut_counts, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_mut_counts, 0, 8 * kMutMaxGroups * sizeof(unsigned long long), ctx->stream));
     const int grid_a = (int)std::min<long long>((N + threads - 1) / threads, (long long)ctx->sm_count * 16);
-    accept_kernel<<<grid_a, threads, 0, ctx->stream>>>(M, mut->beta, (const double*)ctx->m_props.p, (const double*)ctx->m_ll.p,
-                                                       (const uint8_t*)ctx->m_inside.p, (long long)N, (const double*)d_res,
-                                                       (const double*)d_lres, (double*)d_tout, (double*)d_lout, ctx->d_mut_counts);
-    status_count_kernel<<<grid_p, threads, 0, ctx->stream>>>((const uint32_t*)ctx->m_status.p, NK, ctx->d_mut_counts);
+    accept_kernel<<<grid_a, threads, 0, ctx->stream>>>(d_groups, n_groups, (const double*)ctx->m_props.p, (const double*)ctx->m_ll.p,
+                                                       (const uint8_t*)ctx->m_inside.p, N, (const double*)d_res, (const double*)d_lres,
+                                                       (double*)d_tout, (double*)d_lout, ctx->d_mut_counts);
+    status_count_kernel<<<grid_p, threads, 0, ctx->stream>>>(d_groups, n_groups, (const uint32_t*)ctx->m_status.p, NK, ctx->d_mut_counts);
     CU(cudaGetLastError());
     ctx->launches += 2;
     if (h_tout) CU(cudaMemcpyAsync(h_tout, d_tout, (size_t)N * d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -760,17 +775,27 @@ int hmx_mutate(hmx_ctx* ctx, const hmx_mutation* mut, const double* theta_res, c
     if (logL_props)
         CU(cudaMemcpyAsync(logL_props, ctx->m_ll.p, (size_t)NK * sizeof(double),
                            is_device_ptr(logL_props) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
-    unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    CU(cudaMemcpyAsync(h, ctx->d_mut_counts, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<unsigned long long> h(8 * (size_t)n_groups, 0ull);
+    CU(cudaMemcpyAsync(h.data(), ctx->d_mut_counts, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     if (stats) {
-        stats->n_accepted = (int64_t)h[0];
-        stats->n_candidates = (int64_t)h[1];
-        stats->n_nonfinite = (int64_t)h[2];
-        stats->n_maxiter = (int64_t)h[3];
-        stats->n_singular = (int64_t)h[4];
+        for (int g = 0; g < n_groups; ++g) {
+            stats[g].n_accepted = (int64_t)h[8 * g + 0];
+            stats[g].n_candidates = (int64_t)h[8 * g + 1];
+            stats[g].n_nonfinite = (int64_t)h[8 * g + 2];
+            stats[g].n_maxiter = (int64_t)h[8 * g + 3];
+            stats[g].n_singular = (int64_t)h[8 * g + 4];
+        }
     }
     return HMX_OK;
+}
+
+int hmx_mutate(hmx_ctx* ctx, const hmx_mutation* mut, const double* theta_res, const double* logL_res, int64_t N,
+               double* theta_out, double* logL_out, double* props, double* logL_props, hmx_mutation_stats* stats) {
+    if (!ctx) return HMX_ERR_INVALID;
+    if (!mut || N < 0) return fail(ctx, HMX_ERR_INVALID, "hmx_mutate: NULL argument or N < 0");
+    const int64_t n = N;
+    return hmx_mutate_groups(ctx, 1, mut, &n, theta_res, logL_res, theta_out, logL_out, props, logL_props, stats);
 }
 
 int hmx_set_timing(hmx_ctx* ctx, int32_t enabled) {

@@ -196,16 +196,38 @@ inline void make_mutation_params(const hmx_mutation& m, MutationParams& M) {
     M.index_offset = m.index_offset;
 }
 
+// One entry per independent population (chain / condition) handled by a launch: its parameters and where its
+// particles and proposals sit in the concatenated arrays.
+constexpr int kMutMaxGroups = 64;
+struct MutationGroup {
+    MutationParams M;
+    double beta;
+    long long part0, n_part;  // particles [part0, part0 + n_part)
+    long long prop0;          // proposals [prop0, prop0 + n_part * M.K)
+};
+
+// group of a flat index given the ascending start offsets (n_groups <= 64: a linear scan over shared memory)
+HMX_HD int group_of(const long long* start, int n_groups, long long idx) {
+    int g = 0;
+    while (g + 1 < n_groups && idx >= start[g + 1]) ++g;
+    return g;
+}
+
 #if defined(__CUDACC__)
-__global__ void propose_kernel(const __grid_constant__ MutationParams M, const double* __restrict__ theta_res, long long N,
-                               double* __restrict__ props, double* __restrict__ theta_full, int32_t* __restrict__ cond_id,
-                               uint8_t* __restrict__ inside) {
-    const long long total = N * M.K;
+__global__ void propose_kernel(const MutationGroup* __restrict__ groups, int n_groups, const double* __restrict__ theta_res,
+                               long long total, double* __restrict__ props, double* __restrict__ theta_full,
+                               int32_t* __restrict__ cond_id, uint8_t* __restrict__ inside) {
+    __shared__ long long start[kMutMaxGroups];
+    if (threadIdx.x < n_groups) start[threadIdx.x] = groups[threadIdx.x].prop0;
+    __syncthreads();
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const long long i = t / M.K;
+        const MutationGroup& G = groups[group_of(start, n_groups, t)];
+        const MutationParams& M = G.M;
+        const long long tl = t - G.prop0;
+        const long long i = G.part0 + tl / M.K;
         double mean[kMutMaxDim], prop[kMutMaxDim], full[HMX_NTHETA];
         for (int j = 0; j < M.d; ++j) mean[j] = theta_res[i * M.d + j];
-        const uint64_t gidx = (uint64_t)(M.index_offset * (unsigned long long)M.K) + (uint64_t)t;
+        const uint64_t gidx = (uint64_t)(M.index_offset * (unsigned long long)M.K) + (uint64_t)tl;
         const bool in = propose_one(M, mean, gidx, prop);
         for (int j = 0; j < M.d; ++j) props[t * M.d + j] = prop[j];
         const int32_t c = expand_theta(M, prop, full);
@@ -215,50 +237,69 @@ __global__ void propose_kernel(const __grid_constant__ MutationParams M, const d
     }
 }
 
-__global__ void accept_kernel(const __grid_constant__ MutationParams M, double beta, const double* __restrict__ props,
+// counts: [n_groups][8] = accepted, candidates, nonfinite, maxiter, singular
+__global__ void accept_kernel(const MutationGroup* __restrict__ groups, int n_groups, const double* __restrict__ props,
                               const double* __restrict__ ll, const uint8_t* __restrict__ inside, long long N,
                               const double* __restrict__ theta_res, const double* __restrict__ logL_res,
                               double* __restrict__ theta_out, double* __restrict__ logL_out, unsigned long long* counts) {
-    int acc = 0, cand = 0;
+    __shared__ long long start[kMutMaxGroups];
+    if (threadIdx.x < n_groups) start[threadIdx.x] = groups[threadIdx.x].part0;
+    __syncthreads();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const int g = group_of(start, n_groups, i);
+        const MutationGroup& G = groups[g];
+        const MutationParams& M = G.M;
+        const long long il = i - G.part0;
+        const long long p0 = G.prop0 + il * M.K;
         double cur[kMutMaxDim];
         for (int j = 0; j < M.d; ++j) cur[j] = theta_res[i * M.d + j];
         double cl = logL_res[i];
-        accept_chain(M, beta, (uint64_t)(M.index_offset + (unsigned long long)i), props + (size_t)i * M.K * M.d, ll + i * M.K,
-                     inside + i * M.K, cur, cl, acc, cand);
+        int acc = 0, cand = 0;
+        accept_chain(M, G.beta, (uint64_t)(M.index_offset + (unsigned long long)il), props + (size_t)p0 * M.d, ll + p0, inside + p0, cur, cl,
+                     acc, cand);
         for (int j = 0; j < M.d; ++j) theta_out[i * M.d + j] = cur[j];
         logL_out[i] = cl;
-    }
-    // warp-aggregated counters
-    for (int o = 16; o > 0; o >>= 1) {
-        acc += __shfl_down_sync(0xffffffffu, acc, o);
-        cand += __shfl_down_sync(0xffffffffu, cand, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (acc) atomicAdd(counts + 0, (unsigned long long)acc);
-        if (cand) atomicAdd(counts + 1, (unsigned long long)cand);
+        if (acc) atomicAdd(counts + 8 * g + 0, (unsigned long long)acc);
+        if (cand) atomicAdd(counts + 8 * g + 1, (unsigned long long)cand);
     }
 }
 
-// status words of the N K proposal solves -> health counters (EV: LikelihoodHealthCounter)
-__global__ void status_count_kernel(const uint32_t* __restrict__ status, long long n, unsigned long long* counts) {
-    int a = 0, b = 0, c = 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const uint32_t s = status[i];
-        a += (s & 1u) != 0;
-        b += (s & 2u) != 0;
-        c += (s & 4u) != 0;
+// status words of the proposal solves -> health counters per group (EV: LikelihoodHealthCounter)
+__global__ void status_count_kernel(const MutationGroup* __restrict__ groups, int n_groups, const uint32_t* __restrict__ status,
+                                    long long total, unsigned long long* counts) {
+    __shared__ long long start[kMutMaxGroups];
+    if (threadIdx.x < n_groups) start[threadIdx.x] = groups[threadIdx.x].prop0;
+    __syncthreads();
+    int cur = -1, cnt[3] = {0, 0, 0};
+    auto flush = [&]() {
+        // one atomic per warp when every lane holds counts of the same group (the common case), else one per lane
+        const bool uniform = __all_sync(0xffffffffu, cur == __shfl_sync(0xffffffffu, cur, 0));
+        for (int bit = 0; bit < 3; ++bit) {
+            int v = cnt[bit];
+            if (uniform) {
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                if ((threadIdx.x & 31) == 0 && cur >= 0 && v) atomicAdd(counts + 8 * cur + 2 + bit, (unsigned long long)v);
+            } else if (cur >= 0 && v) {
+                atomicAdd(counts + 8 * cur + 2 + bit, (unsigned long long)v);
+            }
+            cnt[bit] = 0;
+        }
+    };
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long rounds = (total + stride - 1) / stride;  // every lane runs the same number of rounds (warp collectives inside)
+    for (long long r = 0; r < rounds; ++r) {
+        const long long t = r * stride + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        const int g = (t < total) ? group_of(start, n_groups, t) : cur;
+        if (__any_sync(0xffffffffu, g != cur && cur >= 0)) flush();
+        cur = g;
+        if (t < total) {
+            const uint32_t s = status[t];
+            cnt[0] += (s & 1u) != 0;
+            cnt[1] += (s & 2u) != 0;
+            cnt[2] += (s & 4u) != 0;
+        }
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        a += __shfl_down_sync(0xffffffffu, a, o);
-        b += __shfl_down_sync(0xffffffffu, b, o);
-        c += __shfl_down_sync(0xffffffffu, c, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (a) atomicAdd(counts + 2, (unsigned long long)a);
-        if (b) atomicAdd(counts + 3, (unsigned long long)b);
-        if (c) atomicAdd(counts + 4, (unsigned long long)c);
-    }
+    flush();
 }
 #endif
 

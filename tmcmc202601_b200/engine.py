@@ -116,6 +116,39 @@ class HamiltonEngine:
         self._check(self._lib.hmx_trajectory_batch(self._ctx, _addr(theta), _addr(cid), N, _addr(g), _addr(status), _addr(iters)), "hmx_trajectory_batch")
         return g, status, iters
 
+    def mutate_groups(self, mutations, theta_list, logL_list):
+        """Several independent populations in one set of launches (hmx_mutate_groups): mutations[g] applies to
+        theta_list[g][N_g, d], logL_list[g][N_g].  Returns a list of (theta_new, logL_new, stats) per group."""
+        G = len(mutations)
+        if not (1 <= G <= _abi.MUT_MAX_GROUPS and len(theta_list) == G and len(logL_list) == G):
+            raise ValueError(f"between 1 and {_abi.MUT_MAX_GROUPS} groups, one (theta, logL) pair each")
+        ths = [np.ascontiguousarray(t, dtype=np.float64) for t in theta_list]
+        lls = [np.ascontiguousarray(l, dtype=np.float64) for l in logL_list]
+        d = mutations[0].d
+        for m, t, l in zip(mutations, ths, lls):
+            if t.ndim != 2 or t.shape[1] != d or m.d != d or l.shape != (t.shape[0],):
+                raise ValueError("every group needs theta (N_g, d) with the common d and logL (N_g,)")
+        theta_res = np.concatenate(ths, axis=0)
+        logL_res = np.concatenate(lls)
+        counts = (C.c_int64 * G)(*[t.shape[0] for t in ths])
+        muts = (_abi.HmxMutation * G)(*mutations)
+        stats = (_abi.HmxMutationStats * G)()
+        theta_out, logL_out = np.empty_like(theta_res), np.empty_like(logL_res)
+        self._check(
+            self._lib.hmx_mutate_groups(self._ctx, G, muts, counts, _addr(theta_res), _addr(logL_res), _addr(theta_out), _addr(logL_out),
+                                        None, None, stats),
+            "hmx_mutate_groups",
+        )
+        out, off = [], 0
+        for g, t in enumerate(ths):
+            n = t.shape[0]
+            st = stats[g]
+            out.append((theta_out[off:off + n].copy(), logL_out[off:off + n].copy(),
+                        {"n_accepted": st.n_accepted, "n_candidates": st.n_candidates, "n_nonfinite": st.n_nonfinite,
+                         "n_maxiter": st.n_maxiter, "n_singular": st.n_singular}))
+            off += n
+        return out
+
     def trajectory_rows(self, theta, rows, cond_id=None):
         """g[N, len(rows), 12]: the time levels `rows` (strictly ascending) of every trajectory (hmx_trajectory_rows)."""
         theta = np.ascontiguousarray(theta, dtype=np.float64)
