@@ -22,6 +22,7 @@
 #include "hmx_kernels.cuh"
 #include "hmx_stage.cuh"
 #include "hmx_mutation.cuh"
+#include "hmx_coop.cuh"
 
 using namespace hmx;
 
@@ -51,6 +52,9 @@ struct hmx_ctx {
     bool alpha = false;
     int hill = 0;
     int ode_blocks_per_sm = 1;
+    int coop_blocks_per_sm = 1;
+    long long coop_max_evals = 0;   // batches up to this size run the 8-lanes-per-solve kernel (HMX_COOP_MAX_EVALS overrides)
+    bool last_kernel_coop = false;
     std::string err;
 
     // device scratch
@@ -163,6 +167,16 @@ void launch_ode(hmx_ctx* ctx, const OdeParams& P, int blocks) {
     ode_kernel<ALPHA, HILL><<<blocks, kOdeThreads, 0, ctx->stream>>>(P);
 }
 template <bool ALPHA, int HILL>
+void launch_coop(hmx_ctx* ctx, const OdeParams& P, int blocks) {
+    coop_ode_kernel<ALPHA, HILL><<<blocks, kCoopThreads, 0, ctx->stream>>>(P);
+}
+template <bool ALPHA, int HILL>
+int coop_occupancy() {
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, coop_ode_kernel<ALPHA, HILL>, kCoopThreads, 0);
+    return nb;
+}
+template <bool ALPHA, int HILL>
 void launch_obs(hmx_ctx* ctx, const ObsParams& P, int blocks) {
     obs_kernel<ALPHA, HILL><<<blocks, 128, 0, ctx->stream>>>(P);
 }
@@ -192,6 +206,16 @@ int query_occupancy(hmx_ctx* ctx) {
         nb = ctx->hill == 0 ? ode_occupancy<true, 0>() : ctx->hill == 1 ? ode_occupancy<true, 1>() : ode_occupancy<true, 2>();
     } else {
         nb = ctx->hill == 0 ? ode_occupancy<false, 0>() : ctx->hill == 1 ? ode_occupancy<false, 1>() : ode_occupancy<false, 2>();
+    }
+    return std::max(nb, 1);
+}
+
+int query_coop_occupancy(hmx_ctx* ctx) {
+    int nb = 0;
+    if (ctx->alpha) {
+        nb = ctx->hill == 0 ? coop_occupancy<true, 0>() : ctx->hill == 1 ? coop_occupancy<true, 1>() : coop_occupancy<true, 2>();
+    } else {
+        nb = ctx->hill == 0 ? coop_occupancy<false, 0>() : ctx->hill == 1 ? coop_occupancy<false, 1>() : coop_occupancy<false, 2>();
     }
     return std::max(nb, 1);
 }
@@ -245,10 +269,20 @@ int run_chunk(hmx_ctx* ctx, const double* d_theta, const int32_t* d_cond, long l
         P.order = (const int*)ctx->order.p;
     }
 
-    const long long want_blocks = (N + kOdeThreads - 1) / kOdeThreads;
-    const int blocks = (int)std::min<long long>(want_blocks, (long long)ctx->sm_count * ctx->ode_blocks_per_sm);
     if (ctx->timing) CU(cudaEventRecord(ctx->ev0, ctx->stream));
-    HMX_DISPATCH(launch_ode, ctx, P, blocks);
+    if (N <= ctx->coop_max_evals) {
+        // latency regime: eight lanes per solve (K1L, hmx_coop.cuh)
+        const int per_cta = kCoopThreads / kCoopLanes;
+        const long long want = (N + per_cta - 1) / per_cta;
+        const int blocks = (int)std::min<long long>(want, (long long)ctx->sm_count * ctx->coop_blocks_per_sm);
+        HMX_DISPATCH(launch_coop, ctx, P, blocks);
+        ctx->last_kernel_coop = true;
+    } else {
+        const long long want_blocks = (N + kOdeThreads - 1) / kOdeThreads;
+        const int blocks = (int)std::min<long long>(want_blocks, (long long)ctx->sm_count * ctx->ode_blocks_per_sm);
+        HMX_DISPATCH(launch_ode, ctx, P, blocks);
+        ctx->last_kernel_coop = false;
+    }
     CU(cudaGetLastError());
     ++ctx->launches;
     if (ctx->timing) {
@@ -400,6 +434,11 @@ int hmx_create(hmx_ctx** out, const hmx_config* cfg, int32_t device) {
     CU_CREATE(cudaEventCreate(&ctx->ev0));
     CU_CREATE(cudaEventCreate(&ctx->ev1));
     ctx->ode_blocks_per_sm = query_occupancy(ctx);
+    ctx->coop_blocks_per_sm = query_coop_occupancy(ctx);
+    // K1L wins while all its groups are resident at once (measured: 1.37x at 1000 evaluations, 1.19x at 7000, break-even
+    // at 10 000): groups resident = SMs x CTAs/SM x 16 = 7104 on a B200
+    ctx->coop_max_evals = 1ll * ctx->sm_count * ctx->coop_blocks_per_sm * (kCoopThreads / kCoopLanes);
+    if (const char* cm = getenv("HMX_COOP_MAX_EVALS")) ctx->coop_max_evals = atoll(cm);  // 0 disables K1L
     if (const char* ce = getenv("HMX_CHUNK_EVALS")) {
         const long long v = atoll(ce);
         if (v > 0) ctx->chunk_evals = v;
