@@ -199,9 +199,9 @@ def tmcmc_run():
 
     out = {"config": "BASELINE.json configs[1]: Dysbiotic HOBIC production run, N=1000 x 2 chains, K=0.05 n=4, seed 42",
            "reference_wall_s": 226864.8}
-    for key, dev in (("host_mutation", False), ("device_mutation", True)):
+    for key, dev, lat in (("host_mutation", False, False), ("device_mutation", True, False), ("device_mutation_latency_kernel", True, True)):
         try:
-            res, samples, ll = rp.run_condition("Dysbiotic_HOBIC_legacy_1k30", 1000, 2, device_mutation=dev)
+            res, samples, ll = rp.run_condition("Dysbiotic_HOBIC_legacy_1k30", 1000, 2, device_mutation=dev, latency_kernel=lat)
             cmp_ = rp.compare_with_reference(samples, ll)
             out[key] = {"wall_s": res["wall_s"], "likelihood_evaluations": res["likelihood_evaluations"], "stages": res["stages"],
                         "converged": res["converged"], "posterior_z_mean_max": cmp_["z_mean_max"],

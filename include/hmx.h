@@ -164,6 +164,12 @@ typedef struct {
 } hmx_counters;
 /* synchronises the stream */
 int hmx_get_counters(hmx_ctx* ctx, hmx_counters* out);
+/* Latency regime (production TMCMC stages: 10^3-10^4 evaluations per launch, which cost the latency of the slowest solve):
+ * batches of at most max_evals evaluations run K1L, eight lanes per solve (csrc/hmx_coop.cuh), 20-37 % faster per launch.
+ * max_evals < 0 selects the measured optimum (one resident round of groups, 7104 on a B200), 0 switches K1L off (default).
+ * K1L agrees with the default kernel to ~1e-12 relative on logL, not bit for bit: with it on, a value may depend (at that
+ * level) on the size of the batch it is evaluated in. */
+int hmx_set_latency_kernel(hmx_ctx* ctx, int64_t max_evals);
 /* enable CUDA-event timing of the ODE kernel inside hmx_loglik_batch (adds two event records) */
 int hmx_set_timing(hmx_ctx* ctx, int32_t enabled);
 /* register-resident DFMA loop: measured FP64 FMA peak of this GPU in TFLOP/s (roofline denominator) */

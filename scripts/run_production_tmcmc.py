@@ -22,7 +22,7 @@ from tmcmc202601_b200 import tmcmc, workloads  # noqa: E402
 from tmcmc202601_b200.evaluator import LogLikelihoodEvaluator  # noqa: E402
 
 
-def run_condition(key, n_particles, n_chains, seed=42, n_mutation_steps=5, n_stages=30, device_mutation=False):
+def run_condition(key, n_particles, n_chains, seed=42, n_mutation_steps=5, n_stages=30, device_mutation=False, latency_kernel=False):
     cd = workloads.load_conditions()[key]
     legacy = key.endswith("legacy_1k30")
     sk = dict(workloads.PRODUCTION_SOLVER, phi_init=0.02 if legacy else cd["phi_init"])
@@ -35,7 +35,7 @@ def run_condition(key, n_particles, n_chains, seed=42, n_mutation_steps=5, n_sta
 
     def make_evaluator(theta_linearization=None):
         ev = LogLikelihoodEvaluator(sk, [0, 1, 2, 3, 4], active, theta_base, cd["data"], cd["idx_sparse"], sigma, cov_rel=0.005,
-                                    theta_linearization=theta_linearization)
+                                    theta_linearization=theta_linearization, latency_kernel=latency_kernel)
         evs.append(ev)
         return ev
 
@@ -51,7 +51,7 @@ def run_condition(key, n_particles, n_chains, seed=42, n_mutation_steps=5, n_sta
     n_evals = sum(ev.health.n_calls for ev in evs)
     gpu_s = sum(ev.timing.get_s("tsm.solve_tsm") for ev in evs)
     out = {
-        "condition": key, "device_mutation": bool(device_mutation), "n_particles": n_particles, "n_chains": n_chains, "seed": seed, "n_mutation_steps": n_mutation_steps,
+        "condition": key, "device_mutation": bool(device_mutation), "latency_kernel": bool(latency_kernel), "n_particles": n_particles, "n_chains": n_chains, "seed": seed, "n_mutation_steps": n_mutation_steps,
         "wall_s": wall, "likelihood_evaluations": int(n_evals), "likelihood_wall_s": gpu_s, "evals_per_s_in_run": n_evals / gpu_s,
         "converged": [bool(c) for c in conv], "stages": [len(s) for s in diag["stage_summaries"]],
         "beta_schedules": diag["beta_schedules"], "acc_rates": diag["acc_rate_histories"], "log_evidence": diag["log_evidence"],
@@ -105,6 +105,7 @@ def main():
     ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "tmcmc_runs.json"))
     ap.add_argument("--only", default=None)
     ap.add_argument("--device-mutation", action="store_true", help="proposals / accept-reject on the GPU (Philox stream)")
+    ap.add_argument("--latency-kernel", action="store_true", help="K1L (eight lanes per solve) for production-sized launches")
     args = ap.parse_args()
     keys = ["Dysbiotic_HOBIC_legacy_1k30"] + workloads.CONDITION_KEYS
     if args.only:
@@ -116,7 +117,7 @@ def main():
         results.append(summary)
         keys = []
     for k in keys:
-        out, samples, ll = run_condition(k, args.particles, args.chains, device_mutation=args.device_mutation)
+        out, samples, ll = run_condition(k, args.particles, args.chains, device_mutation=args.device_mutation, latency_kernel=args.latency_kernel)
         if k.endswith("legacy_1k30") and args.particles >= 500:
             out["vs_reference_run"] = compare_with_reference(samples, ll)
         print(json.dumps({kk: out[kk] for kk in ("condition", "wall_s", "likelihood_evaluations", "stages", "logL_max", "Rhat_max") if kk in out}

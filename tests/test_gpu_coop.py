@@ -61,14 +61,18 @@ def test_coop_kernel_trajectories_and_work_queue(built, monkeypatch):
     assert np.array_equal(coop[1][:, 0, :5], np.tile(np.array([c.phi_init[:] for c in wl.config.cond[:4]])[wl.cond_id[:300]], 1))
 
 
-def test_default_switch_between_the_kernels(built):
-    """Without the override small batches take K1L and large ones K1; both paths give the same numbers."""
+def test_latency_kernel_switch(built):
+    """hmx_set_latency_kernel(-1): small batches take K1L and large ones K1; off by default (bitwise batch independence)."""
     wl = workloads.four_condition_workload(2000, seed=3, solver=dict(workloads.PRODUCTION_SOLVER, maxtimestep=30))
     for k in range(4):
         for o, v in enumerate([3, 8, 14, 22, 29]):
             wl.config.cond[k].idx_sparse[o] = v
     eng = HamiltonEngine(wl.config, 0)
     big = eng.loglik_batch(wl.theta, wl.cond_id)            # 8000 evaluations: K1
+    small_default = eng.loglik_batch(wl.theta[:500], wl.cond_id[:500])
+    assert np.array_equal(big[:500], small_default)         # default: one kernel, values independent of the batch
+    eng.set_latency_kernel(-1)
     small = eng.loglik_batch(wl.theta[:500], wl.cond_id[:500])  # K1L
+    assert np.array_equal(eng.loglik_batch(wl.theta, wl.cond_id), big)  # above the limit: still K1
     eng.close()
     assert np.allclose(big[:500], small, rtol=1e-10)

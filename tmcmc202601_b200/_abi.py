@@ -146,7 +146,7 @@ EXPORTS = [
     "hmx_weighted_cov", "hmx_weighted_moments", "hmx_weighted_scatter", "hmx_log_likelihood_sparse", "hmx_get_counters",
     "hmx_set_timing",
     "hmx_measure_fp64_peak",
-    "hmx_mutate", "hmx_mutate_groups", "hmx_trajectory_rows",
+    "hmx_mutate", "hmx_mutate_groups", "hmx_trajectory_rows", "hmx_set_latency_kernel",
 ]
 
 
@@ -288,6 +288,7 @@ def load() -> C.CDLL:
     lib.hmx_log_likelihood_sparse.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int32, vp]
     lib.hmx_get_counters.argtypes = [vp, C.POINTER(HmxCounters)]
     lib.hmx_set_timing.argtypes = [vp, C.c_int32]
+    lib.hmx_set_latency_kernel.argtypes = [vp, C.c_int64]
     lib.hmx_measure_fp64_peak.argtypes = [vp, dp]
     lib.hmx_mutate.argtypes = [vp, C.POINTER(HmxMutation), vp, vp, C.c_int64, vp, vp, vp, vp, C.POINTER(HmxMutationStats)]
     lib.hmx_mutate_groups.argtypes = [vp, C.c_int32, C.POINTER(HmxMutation), lp, vp, vp, vp, vp, vp, vp, C.POINTER(HmxMutationStats)]

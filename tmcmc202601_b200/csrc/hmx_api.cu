@@ -435,10 +435,11 @@ int hmx_create(hmx_ctx** out, const hmx_config* cfg, int32_t device) {
     CU_CREATE(cudaEventCreate(&ctx->ev1));
     ctx->ode_blocks_per_sm = query_occupancy(ctx);
     ctx->coop_blocks_per_sm = query_coop_occupancy(ctx);
-    // K1L wins while all its groups are resident at once (measured: 1.37x at 1000 evaluations, 1.19x at 7000, break-even
-    // at 10 000): groups resident = SMs x CTAs/SM x 16 = 7104 on a B200
-    ctx->coop_max_evals = 1ll * ctx->sm_count * ctx->coop_blocks_per_sm * (kCoopThreads / kCoopLanes);
-    if (const char* cm = getenv("HMX_COOP_MAX_EVALS")) ctx->coop_max_evals = atoll(cm);  // 0 disables K1L
+    // K1L is OPT-IN (hmx_set_latency_kernel / HMX_COOP_MAX_EVALS): it agrees with K1 to ~1e-12, not bit for bit, so a
+    // size-dependent switch would make a likelihood depend on the size of the batch it travels in -- and with it the
+    // guarantees "merged launches == separate launches" and "sharded == single GPU" (both bitwise) would go.
+    ctx->coop_max_evals = 0;
+    if (const char* cm = getenv("HMX_COOP_MAX_EVALS")) ctx->coop_max_evals = atoll(cm);
     if (const char* ce = getenv("HMX_CHUNK_EVALS")) {
         const long long v = atoll(ce);
         if (v > 0) ctx->chunk_evals = v;
@@ -835,6 +836,13 @@ int hmx_mutate(hmx_ctx* ctx, const hmx_mutation* mut, const double* theta_res, c
     if (!mut || N < 0) return fail(ctx, HMX_ERR_INVALID, "hmx_mutate: NULL argument or N < 0");
     const int64_t n = N;
     return hmx_mutate_groups(ctx, 1, mut, &n, theta_res, logL_res, theta_out, logL_out, props, logL_props, stats);
+}
+
+int hmx_set_latency_kernel(hmx_ctx* ctx, int64_t max_evals) {
+    if (!ctx) return HMX_ERR_INVALID;
+    // < 0: the measured sweet spot, one resident round of 8-lane groups (7104 evaluations on a B200)
+    ctx->coop_max_evals = max_evals < 0 ? 1ll * ctx->sm_count * ctx->coop_blocks_per_sm * (kCoopThreads / kCoopLanes) : max_evals;
+    return HMX_OK;
 }
 
 int hmx_set_timing(hmx_ctx* ctx, int32_t enabled) {
