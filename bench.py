@@ -201,9 +201,13 @@ def tmcmc_run():
            "reference_wall_s": 226864.8}
     for key, dev, lat in (("host_mutation", False, False), ("device_mutation", True, False), ("device_mutation_latency_kernel", True, True)):
         try:
-            res, samples, ll = rp.run_condition("Dysbiotic_HOBIC_legacy_1k30", 1000, 2, device_mutation=dev, latency_kernel=lat)
+            # two runs, the faster one reported: the first pays one-off costs (lazy kernel loading, buffer growth)
+            walls = []
+            for _ in range(2):
+                res, samples, ll = rp.run_condition("Dysbiotic_HOBIC_legacy_1k30", 1000, 2, device_mutation=dev, latency_kernel=lat)
+                walls.append(res["wall_s"])
             cmp_ = rp.compare_with_reference(samples, ll)
-            out[key] = {"wall_s": res["wall_s"], "likelihood_evaluations": res["likelihood_evaluations"], "stages": res["stages"],
+            out[key] = {"wall_s": min(walls), "wall_s_first_run": walls[0], "likelihood_evaluations": res["likelihood_evaluations"], "stages": res["stages"],
                         "converged": res["converged"], "posterior_z_mean_max": cmp_["z_mean_max"],
                         "posterior_std_ratio": [cmp_["std_ratio_min"], cmp_["std_ratio_max"]], "logL_max": res["logL_max"]}
         except Exception as e:  # the throughput line must not be lost to a failure of the side measurement
