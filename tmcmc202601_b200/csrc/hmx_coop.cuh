@@ -314,6 +314,10 @@ __global__ void __launch_bounds__(kCoopThreads) coop_ode_kernel(const __grid_con
     long long pos = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kCoopLanes;
 
     CoopConsts C;
+    // groups that never receive work still run the shuffles with the warp: give them a benign system (S = I)
+    C.inv_eta = C.etaphi_eta = C.c_eta = C.alpha_eta = C.b = C.a_diag = 0.0;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) C.a_row[j] = 0.0;
     double g_ph = 0.0, g_ps = 0.0, gp_ph = 0.0, gp_ps = 0.0, d_ph = 0.0, d_ps = 0.0;
     double normQ = 0.0, step = 1.0, tol = 0.0;
     int step_idx = 0, it = 0, mode = kModeEval;
