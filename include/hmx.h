@@ -133,6 +133,9 @@ int hmx_beta_step(hmx_ctx* ctx, const double* logL, int64_t N, double beta, doub
 /* replaces: weights + evidence increment (TM:686-701). delta_beta is (beta_next - beta) as the reference
  * forms it.  *log_Sj is NaN and w uniform when the reference would fall back ("Weight sum issue"). */
 int hmx_weights(hmx_ctx* ctx, const double* logL, int64_t N, double delta_beta, double* w, double* log_Sj);
+/* cs = np.cumsum(w) bit for bit (the sequentially rounded chain of tmcmc.py:195), with cs[N-1] := 1.0 (tmcmc.py:196).
+ * Computed tile-parallel where that is provably equal to the chain, as the literal chain elsewhere (csrc/hmx_stage.cuh). */
+int hmx_cumsum(hmx_ctx* ctx, const double* w, int64_t N, double* cs);
 /* replaces: systematic_resample (TM:186-198) with the uniform draw u = rng.random() supplied by the host.
  * idx [N] int64, bit-exact with NumPy for identical (w, u). */
 int hmx_resample(hmx_ctx* ctx, const double* w, int64_t N, double u, int64_t* idx);

@@ -113,3 +113,44 @@ def test_systematic_resample_api(eng):
     idx = systematic_resample(w, np.random.default_rng(42))
     u = np.random.default_rng(42).random()
     assert np.array_equal(idx, orc.resample(w, u))
+
+
+def test_cumsum_equals_numpy_chain_bitwise_on_adversarial_weights(eng):
+    """hmx_cumsum == np.cumsum bit for bit.  The kernel handles tiles in parallel only where that provably equals the
+    sequentially rounded chain; the cases below hit every fall-back: binade crossings, exact rounding ties, weights
+    heavier than the running sum, zeros, subnormals, sorted and wildly uneven weights, ragged last tiles."""
+    rng = np.random.default_rng(0)
+    cases = {}
+    w = rng.random(300001)
+    cases["uniform"] = w / w.sum()
+    w = np.exp(rng.normal(size=262144) * 6)
+    cases["lognormal"] = w / w.sum()
+    w = np.sort(np.exp(rng.normal(size=100000) * 10))
+    cases["ascending"] = w / w.sum()
+    cases["descending"] = cases["ascending"][::-1].copy()
+    cases["constant"] = np.full(200000, 1.0 / 200000)
+    w = rng.random(100000)
+    w[rng.random(100000) < 0.3] = 0.0
+    cases["zeros"] = w / w.sum()
+    cases["ties"] = np.concatenate([[0.6], (rng.integers(1, 1000, 50000) + 0.5) * 2.0 ** -53, rng.random(1000) * 1e-6])
+    cases["subnormal"] = np.concatenate([np.full(5000, 5e-324), np.full(5000, 1e-310), rng.random(50000) * 1e-5])
+    cases["jumps"] = np.concatenate([rng.random(30000) * 1e-9, [0.7], rng.random(30000) * 1e-9, [0.2999], rng.random(30000) * 1e-7])
+    cases["heavy"] = np.concatenate([[1e-3], np.full(5000, 4e-4), rng.random(20000) * 1e-6])
+    cases["tiny"] = np.array([0.25, 0.5, 0.25])
+    cases["single"] = np.array([1.0])
+    w = rng.random(2_000_000)
+    cases["two_million"] = w / w.sum()
+    for name, w in cases.items():
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        ref = np.cumsum(w)
+        ref[-1] = 1.0
+        got = eng.cumsum(w)
+        assert np.array_equal(got.view(np.uint64), ref.view(np.uint64)), name
+    # and the resampling indices that depend on it
+    for name in ("uniform", "lognormal", "ties", "two_million"):
+        w = cases[name] / cases[name].sum()
+        u = float(rng.random())
+        cs = np.cumsum(w)
+        cs[-1] = 1.0
+        want = np.clip(np.searchsorted(cs, (u + np.arange(len(w))) / len(w)), 0, len(w) - 1)
+        assert np.array_equal(eng.resample(w, u), want), name

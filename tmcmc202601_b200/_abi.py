@@ -146,7 +146,7 @@ EXPORTS = [
     "hmx_weighted_cov", "hmx_weighted_moments", "hmx_weighted_scatter", "hmx_log_likelihood_sparse", "hmx_get_counters",
     "hmx_set_timing",
     "hmx_measure_fp64_peak",
-    "hmx_mutate", "hmx_mutate_groups", "hmx_trajectory_rows", "hmx_set_latency_kernel",
+    "hmx_mutate", "hmx_mutate_groups", "hmx_trajectory_rows", "hmx_set_latency_kernel", "hmx_cumsum",
 ]
 
 
@@ -282,6 +282,7 @@ def load() -> C.CDLL:
     lib.hmx_beta_step.argtypes = [vp, vp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp]
     lib.hmx_weights.argtypes = [vp, vp, C.c_int64, C.c_double, vp, vp]
     lib.hmx_resample.argtypes = [vp, vp, C.c_int64, C.c_double, vp]
+    lib.hmx_cumsum.argtypes = [vp, vp, C.c_int64, vp]
     lib.hmx_weighted_cov.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp, vp]
     lib.hmx_weighted_moments.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp]
     lib.hmx_weighted_scatter.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp, vp]

@@ -590,6 +590,25 @@ int hmx_weights(hmx_ctx* ctx, const double* logL, int64_t N, double delta_beta, 
     return HMX_OK;
 }
 
+int hmx_cumsum(hmx_ctx* ctx, const double* w, int64_t N, double* cs) {
+    if (!ctx) return HMX_ERR_INVALID;
+    if (N <= 0 || !w || !cs) return fail(ctx, HMX_ERR_INVALID, "hmx_cumsum: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    const void* d_w;
+    void *d_cs, *h_cs;
+    if ((rc = stage_in(ctx, w, (size_t)N * sizeof(double), ctx->st_in0, &d_w))) return rc;
+    if ((rc = stage_out(ctx, cs, (size_t)N * sizeof(double), ctx->cs, &d_cs, &h_cs))) return rc;
+    cumsum_serial_kernel<<<1, kRedThreads, 0, ctx->stream>>>((const double*)d_w, N, (double*)d_cs);
+    CU(cudaGetLastError());
+    ++ctx->launches;
+    if (h_cs) {
+        CU(cudaMemcpyAsync(h_cs, d_cs, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return HMX_OK;
+}
+
 int hmx_resample(hmx_ctx* ctx, const double* w, int64_t N, double u, int64_t* idx) {
     if (!ctx) return HMX_ERR_INVALID;
     if (N <= 0 || !w || !idx) return fail(ctx, HMX_ERR_INVALID, "hmx_resample: bad arguments");

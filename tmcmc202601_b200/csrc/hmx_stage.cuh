@@ -177,38 +177,115 @@ __global__ void __launch_bounds__(kRedThreads) weights_norm_kernel(double* __res
 }
 
 // K4a: cs = np.cumsum(w) with the exact left-to-right association, cs[N-1] := 1.0  (TM:195-197).
-// The running sum is one chain of N dependent FP64 adds (any re-association could move a resampling index), so
-// the floor is N x DADD latency.  One CTA: all threads stage a tile of w in shared memory (coalesced), thread 0
-// walks the tile with the carry in a register (operands come from shared memory, off the dependency chain),
-// all threads write the prefixes back (coalesced).
+// np.cumsum is one chain of N dependent, individually rounded FP64 adds; re-associating it could move a resampling
+// index, so the result must equal that chain bit for bit.  It does NOT have to be computed as a chain, though:
+// while the running sum s = S u stays inside one binade [2^e, 2^(e+1)) (u = 2^(e-52) its ulp, S an integer), adding a
+// non-negative w that is not an exact tie gives RN(s + w) = (S + q) u with q = RN(w / u) -- the rounding of each
+// addend does not depend on the running sum.  So a tile of 4096 weights is handled in parallel: every thread rounds
+// its 16 weights to integers q (bit operations on the mantissa), an integer block scan gives the prefixes, and the
+// doubles are assembled from (e, S + prefix) directly.  A tile that contains a tie (w / u has fractional part exactly
+// 1/2: the result would depend on the parity of S), a binade crossing, or anything unusual (negative, non-finite,
+// subnormal running sum) is walked by thread 0 as the literal dependent chain, ~11 clk per element.  For N = 2^21
+// normalised weights ~3 % of the tiles take the chain (the binade crossings sit in the first 1/2^k of the array):
+// 1.3 ms instead of 11.7 ms.  Equality with np.cumsum is tested bitwise on adversarial inputs (ties, crossings,
+// sorted / zero / subnormal weights) in tests/test_gpu_stage.py; scripts in tests/tools reproduce it in NumPy.
 constexpr int kCumsumTile = 4096;
+constexpr int kCumsumPerThread = kCumsumTile / kRedThreads;  // 16 contiguous weights per thread
+static_assert(kCumsumPerThread * kRedThreads == kCumsumTile, "tile must be a multiple of the block size");
+
+// q = RN(w / 2^(e-1075)) for a non-negative finite w; flags an exact tie or a weight above the binade of s
+__device__ __forceinline__ unsigned long long cumsum_round_weight(double w, int e, bool& bad) {
+    const unsigned long long wb = (unsigned long long)__double_as_longlong(w);
+    const int ew = (int)((wb >> 52) & 0x7ffull);
+    if ((wb >> 63) || ew == 0x7ff) {
+        bad = true;
+        return 0ull;
+    }
+    const unsigned long long mw = (wb & ((1ull << 52) - 1)) | (ew > 0 ? (1ull << 52) : 0ull);
+    const int sh = e - (ew > 0 ? ew : 1);  // w = mw 2^(ew-1075); u = 2^(e-1075)
+    if (sh < 2) {
+        bad = true;  // at least a quarter of the running sum: (almost) certainly a binade crossing; also keeps 4096 q < 2^64
+        return 0ull;
+    }
+    if (sh >= 64) return 0ull;  // mw < 2^53 <= 2^(sh-1): rounds to zero, cannot tie
+    const unsigned long long fl = mw >> sh;
+    const unsigned long long rem = mw - (fl << sh);
+    const unsigned long long half = 1ull << (sh - 1);
+    if (rem == half) bad = true;  // exact tie: the rounding direction depends on the parity of the running sum
+    return fl + (rem > half ? 1ull : 0ull);
+}
+
 __global__ void __launch_bounds__(kRedThreads) cumsum_serial_kernel(const double* __restrict__ w, long long N, double* __restrict__ cs) {
     __shared__ double tile[kCumsumTile];
-    double carry = 0.0;
+    __shared__ unsigned long long warp_tot[kRedThreads / 32];
+    __shared__ double carry_sh;
+    if (threadIdx.x == 0) carry_sh = 0.0;
+    __syncthreads();
     for (long long base = 0; base < N; base += kCumsumTile) {
         const int n = (int)((N - base < kCumsumTile) ? (N - base) : kCumsumTile);
-        for (int t = threadIdx.x; t < n; t += blockDim.x) tile[t] = w[base + t];
+        for (int t = threadIdx.x; t < kCumsumTile; t += blockDim.x) tile[t] = (t < n) ? w[base + t] : 0.0;
         __syncthreads();
-        if (threadIdx.x == 0) {
+        const double carry = carry_sh;
+        // ---- parallel attempt ----
+        const unsigned long long sb = (unsigned long long)__double_as_longlong(carry);
+        const int e = (int)((sb >> 52) & 0x7ffull);
+        bool bad = (sb >> 63) || e == 0 || e == 0x7ff;  // zero / subnormal / negative / non-finite running sum
+        const unsigned long long S = (sb & ((1ull << 52) - 1)) | (1ull << 52);
+        unsigned long long pre[kCumsumPerThread];
+        unsigned long long run = 0ull;
+        const int t0 = threadIdx.x * kCumsumPerThread;
+#pragma unroll
+        for (int j = 0; j < kCumsumPerThread; ++j) {
+            run += cumsum_round_weight(tile[t0 + j], e > 0 ? e : 1, bad);
+            pre[j] = run;
+        }
+        // exclusive scan of the per-thread totals over the block
+        unsigned long long incl = run;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += v;
+        }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+        const int any_bad = __syncthreads_or(bad ? 1 : 0);
+        unsigned long long offset = incl - run, total = 0ull;
+        for (int k = 0; k < kRedThreads / 32; ++k) {
+            const unsigned long long wt = warp_tot[k];
+            if (k < (int)(threadIdx.x >> 5)) offset += wt;
+            total += wt;
+        }
+        const bool fast = !any_bad && (total < (1ull << 53)) && (S + total < (1ull << 53));
+        if (fast) {
+            const unsigned long long ebits = (unsigned long long)e << 52;
+#pragma unroll
+            for (int j = 0; j < kCumsumPerThread; ++j) {
+                const unsigned long long tot = S + offset + pre[j];  // in [2^52, 2^53): the mantissa with its hidden bit
+                tile[t0 + j] = __longlong_as_double((long long)(ebits | (tot & ((1ull << 52) - 1))));
+            }
+        }
+        __syncthreads();
+        if (!fast && threadIdx.x == 0) {
+            // the literal chain (operands come from shared memory, off the dependency chain)
+            double c = carry;
             int t = 0;
             for (; t + 8 <= n; t += 8) {
                 const double x0 = tile[t], x1 = tile[t + 1], x2 = tile[t + 2], x3 = tile[t + 3];
                 const double x4 = tile[t + 4], x5 = tile[t + 5], x6 = tile[t + 6], x7 = tile[t + 7];
-                carry = __dadd_rn(carry, x0); tile[t] = carry;
-                carry = __dadd_rn(carry, x1); tile[t + 1] = carry;
-                carry = __dadd_rn(carry, x2); tile[t + 2] = carry;
-                carry = __dadd_rn(carry, x3); tile[t + 3] = carry;
-                carry = __dadd_rn(carry, x4); tile[t + 4] = carry;
-                carry = __dadd_rn(carry, x5); tile[t + 5] = carry;
-                carry = __dadd_rn(carry, x6); tile[t + 6] = carry;
-                carry = __dadd_rn(carry, x7); tile[t + 7] = carry;
+                c = __dadd_rn(c, x0); tile[t] = c;
+                c = __dadd_rn(c, x1); tile[t + 1] = c;
+                c = __dadd_rn(c, x2); tile[t + 2] = c;
+                c = __dadd_rn(c, x3); tile[t + 3] = c;
+                c = __dadd_rn(c, x4); tile[t + 4] = c;
+                c = __dadd_rn(c, x5); tile[t + 5] = c;
+                c = __dadd_rn(c, x6); tile[t + 6] = c;
+                c = __dadd_rn(c, x7); tile[t + 7] = c;
             }
             for (; t < n; ++t) {
-                carry = __dadd_rn(carry, tile[t]);
-                tile[t] = carry;
+                c = __dadd_rn(c, tile[t]);
+                tile[t] = c;
             }
         }
         __syncthreads();
+        if (threadIdx.x == 0) carry_sh = tile[n - 1];
         for (int t = threadIdx.x; t < n; t += blockDim.x) cs[base + t] = (base + t == N - 1) ? 1.0 : tile[t];
         __syncthreads();
     }

@@ -204,6 +204,13 @@ class HamiltonEngine:
         self._check(self._lib.hmx_weights(self._ctx, _addr(logL), logL.shape[0], delta_beta, _addr(w), C.addressof(ls)), "hmx_weights")
         return w, ls.value
 
+    def cumsum(self, w):
+        """np.cumsum(w) bit for bit with the last entry forced to 1.0 (hmx_cumsum; the first half of systematic_resample)."""
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        cs = np.empty_like(w)
+        self._check(self._lib.hmx_cumsum(self._ctx, _addr(w), w.shape[0], _addr(cs)), "hmx_cumsum")
+        return cs
+
     def resample(self, w, u):
         w = np.ascontiguousarray(w, dtype=np.float64)
         idx = np.empty(w.shape[0], dtype=np.int64)
