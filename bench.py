@@ -58,7 +58,7 @@ UNIT = "evals/s"
 FLOPS_PER_RESIDUAL = 457.0
 FLOPS_PER_DIRECTION = 850.0
 # DRAM bytes per evaluation of the same capture (dram__bytes_read.sum + dram__bytes_write.sum) / 262144
-DRAM_BYTES_PER_EVAL_NCU = 1134.0
+DRAM_BYTES_PER_EVAL_NCU = 1041  # dram__bytes_read.sum + dram__bytes_write.sum of ode_kernel per evaluation, ncu --set full (profiles/r01j_ode_kernel_rebased.json: 59.5 + 213.3 MB for 262 144 evaluations)
 # the reference-equivalent count of SURVEY.md section 8(d): dense Q + K + dgesv per iteration, Q per extra trial
 REF_FLOPS_PER_ITER = 2778.0
 REF_FLOPS_PER_TRIAL = 384.0
@@ -385,7 +385,7 @@ def main():
     roofline = {
         "bound": "fp64", "kernel": "hmx::ode_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
         "frac": achieved / fp64_peak if fp64_peak > 0 else None,
-        "traffic": DRAM_BYTES_PER_EVAL_NCU * M,  # bytes per launch; ncu measured 1134 B/evaluation, algorithmic 1144
+        "traffic": DRAM_BYTES_PER_EVAL_NCU * M,  # bytes per launch; ncu measured 1041 B/evaluation, algorithmic 1144
         "peak_source": "measured live by hmx_measure_fp64_peak (register-resident DFMA loop); MEASURED_PEAKS.json has no FP64 entry "
                        "(nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2)",
         "kernel_ms_per_launch": ode_avg_ms, "kernel_share_of_step": ode_avg_ms * args.steps / elapsed_ms,
