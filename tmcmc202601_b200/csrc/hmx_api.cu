@@ -58,8 +58,8 @@ struct hmx_ctx {
     std::string err;
 
     // device scratch
-    DevBuf theta, cond_id, pairs, status, iters, trips, logL, obs_state, traj;
-    DevBuf st_in0, st_in1, st_in2, st_out0, st_out1, partial, cs, order;
+    DevBuf theta, cond_id, pairs, status, iters, trips, logL, obs_state, traj, sig2, x1;
+    DevBuf st_in0, st_in1, st_in2, st_out0, st_out1, partial, cs, order, logL_scratch;
     DevBuf m_props, m_theta, m_cond, m_inside, m_ll, m_status, m_in_theta, m_in_logL, m_out_theta, m_out_logL, m_groups;  // hmx_mutate
     unsigned long long* d_mut_counts = nullptr;  // [8] accepted, candidates, nonfinite, maxiter, singular
     SchedState* d_sched = nullptr;
@@ -73,6 +73,7 @@ struct hmx_ctx {
     bool timing = false;
     bool timing_pending = false;
     double last_ode_ms = 0.0;
+    double ode_ms_acc = 0.0;  // ODE kernel time of the chunks of the batch in flight that have already been read
     long long last_evals = 0;
     long long chunk_evals = kDefaultChunkEvals;  // HMX_CHUNK_EVALS overrides (tests exercise the multi-chunk path with it)
     long long launches = 0;
@@ -222,7 +223,8 @@ int query_coop_occupancy(hmx_ctx* ctx) {
 
 // the ODE solve + observation likelihood for one chunk of evaluations already resident on the device
 int run_chunk(hmx_ctx* ctx, const double* d_theta, const int32_t* d_cond, long long N, double* d_logL,
-              double* d_obs_state, uint32_t* d_status, uint32_t* d_iters, double* d_traj, bool want_logL) {
+              double* d_obs_state, uint32_t* d_status, uint32_t* d_iters, double* d_traj, bool want_logL,
+              double* d_sigma2 = nullptr, double* d_x1 = nullptr) {
     int rc;
     const long long pair_stride = (long long)std::max(ctx->n_obs_max, 1) * kPairStride;
     if ((rc = ensure(ctx, ctx->pairs, (size_t)N * pair_stride * sizeof(double)))) return rc;
@@ -269,7 +271,17 @@ int run_chunk(hmx_ctx* ctx, const double* d_theta, const int32_t* d_cond, long l
         P.order = (const int*)ctx->order.p;
     }
 
-    if (ctx->timing) CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (ctx->timing) {
+        // one event pair per context: fold the previous chunk's duration into the running sum before re-recording
+        if (ctx->timing_pending) {
+            float ms = 0.f;
+            CU(cudaEventSynchronize(ctx->ev1));
+            if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->ode_ms_acc += ms;
+            else cudaGetLastError();
+            ctx->timing_pending = false;
+        }
+        CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    }
     if (N <= ctx->coop_max_evals) {
         // latency regime: eight lanes per solve (K1L, hmx_coop.cuh)
         const int per_cta = kCoopThreads / kCoopLanes;
@@ -309,6 +321,8 @@ int run_chunk(hmx_ctx* ctx, const double* d_theta, const int32_t* d_cond, long l
         O.logL = d_logL;
         O.obs_state = d_obs_state;
         O.obs_stride = (long long)std::max(ctx->n_obs_max, 1) * 12;
+        O.sigma2 = d_sigma2;
+        O.x1 = d_x1;
         O.n_cond = ctx->cfg.n_cond;
         const int ob = (int)((N + 127) / 128);
         HMX_DISPATCH(launch_obs, ctx, O, ob);
@@ -319,11 +333,23 @@ int run_chunk(hmx_ctx* ctx, const double* d_theta, const int32_t* d_cond, long l
 }
 
 int batch_impl(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, long long N, double* logL,
-               double* obs_state, uint32_t* status, uint32_t* newton_iters, double* traj) {
+               double* obs_state, uint32_t* status, uint32_t* newton_iters, double* traj, double* sigma2 = nullptr,
+               double* x1 = nullptr) {
     if (!ctx) return HMX_ERR_INVALID;
     if (N < 0 || (N > 0 && !theta)) return fail(ctx, HMX_ERR_INVALID, "theta is NULL or N < 0");
     if (!traj && !logL && N > 0) return fail(ctx, HMX_ERR_INVALID, "logL is NULL");
     CU(cudaSetDevice(ctx->device));
+    if (cond_id && N > 0 && !is_device_ptr(cond_id)) {
+        // a host array is checked here; a device array is checked by the kernels (HMX_ST_BAD_COND, logL = -1e20)
+        for (long long i = 0; i < N; ++i)
+            if (cond_id[i] < 0 || cond_id[i] >= ctx->cfg.n_cond)
+                return fail(ctx, HMX_ERR_INVALID, "cond_id[" + std::to_string(i) + "] = " + std::to_string(cond_id[i]) +
+                                                      " outside [0, n_cond)");
+    }
+    if (ctx->timing_pending) {  // an unread timing of an earlier batch is dropped, not added to this one
+        ctx->timing_pending = false;
+    }
+    ctx->ode_ms_acc = 0.0;
     ctx->last_evals = N;
     CU(cudaMemsetAsync(ctx->d_counters + 1, 0, 2 * sizeof(unsigned long long), ctx->stream));
     if (N == 0) return 0;
@@ -336,8 +362,8 @@ int batch_impl(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, long l
         const long long n = std::min(chunk, N - off);
         int rc;
         const void *d_theta, *d_cond;
-        void *d_logL, *d_obs, *d_status, *d_iters, *d_traj;
-        void *h_logL, *h_obs, *h_status, *h_iters, *h_traj;
+        void *d_logL, *d_obs, *d_status, *d_iters, *d_traj, *d_sig2, *d_x1;
+        void *h_logL, *h_obs, *h_status, *h_iters, *h_traj, *h_sig2, *h_x1;
         if ((rc = stage_in(ctx, theta + off * HMX_NTHETA, (size_t)n * HMX_NTHETA * sizeof(double), ctx->theta, &d_theta))) return rc;
         if ((rc = stage_in(ctx, cond_id ? cond_id + off : nullptr, (size_t)n * sizeof(int32_t), ctx->cond_id, &d_cond))) return rc;
         if ((rc = stage_out(ctx, logL ? logL + off : nullptr, (size_t)n * sizeof(double), ctx->logL, &d_logL, &h_logL))) return rc;
@@ -347,15 +373,22 @@ int batch_impl(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, long l
         if ((rc = stage_out(ctx, newton_iters ? newton_iters + off : nullptr, (size_t)n * sizeof(uint32_t), ctx->st_out1, &d_iters, &h_iters))) return rc;
         if ((rc = stage_out(ctx, traj ? traj + off * traj_stride : nullptr, (size_t)n * traj_stride * sizeof(double), ctx->traj,
                             &d_traj, &h_traj))) return rc;
+        if ((rc = stage_out(ctx, sigma2 ? sigma2 + off * obs_stride : nullptr, (size_t)n * obs_stride * sizeof(double),
+                            ctx->sig2, &d_sig2, &h_sig2))) return rc;
+        if ((rc = stage_out(ctx, x1 ? x1 + off * obs_stride * HMX_NTHETA : nullptr,
+                            (size_t)n * obs_stride * HMX_NTHETA * sizeof(double), ctx->x1, &d_x1, &h_x1))) return rc;
         if (!traj && !d_logL) return fail(ctx, HMX_ERR_INVALID, "logL is NULL");
         if ((rc = run_chunk(ctx, (const double*)d_theta, (const int32_t*)d_cond, n, (double*)d_logL, (double*)d_obs,
-                            (uint32_t*)d_status, (uint32_t*)d_iters, (double*)d_traj, d_logL != nullptr))) return rc;
+                            (uint32_t*)d_status, (uint32_t*)d_iters, (double*)d_traj, d_logL != nullptr, (double*)d_sig2,
+                            (double*)d_x1))) return rc;
+        if (h_sig2) CU(cudaMemcpyAsync(h_sig2, d_sig2, (size_t)n * obs_stride * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (h_x1) CU(cudaMemcpyAsync(h_x1, d_x1, (size_t)n * obs_stride * HMX_NTHETA * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         if (h_logL) CU(cudaMemcpyAsync(h_logL, d_logL, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         if (h_obs) CU(cudaMemcpyAsync(h_obs, d_obs, (size_t)n * obs_stride * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         if (h_status) CU(cudaMemcpyAsync(h_status, d_status, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         if (h_iters) CU(cudaMemcpyAsync(h_iters, d_iters, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         if (h_traj) CU(cudaMemcpyAsync(h_traj, d_traj, (size_t)n * traj_stride * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        const bool any_host = h_logL || h_obs || h_status || h_iters || h_traj;
+        const bool any_host = h_logL || h_obs || h_status || h_iters || h_traj || h_sig2 || h_x1;
         need_sync = need_sync || any_host;
         // staging buffers are reused by the next chunk: drain before overwriting them
         if (off + chunk < N && (any_host || !is_device_ptr(theta))) CU(cudaStreamSynchronize(ctx->stream));
@@ -453,9 +486,9 @@ void hmx_destroy(hmx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->theta, &ctx->cond_id, &ctx->pairs, &ctx->status, &ctx->iters, &ctx->trips, &ctx->logL,
-                      &ctx->obs_state, &ctx->traj, &ctx->st_in0, &ctx->st_in1, &ctx->st_in2, &ctx->st_out0, &ctx->st_out1,
+                      &ctx->obs_state, &ctx->traj, &ctx->sig2, &ctx->x1, &ctx->st_in0, &ctx->st_in1, &ctx->st_in2, &ctx->st_out0, &ctx->st_out1,
                       &ctx->partial, &ctx->cs, &ctx->order, &ctx->m_props, &ctx->m_theta, &ctx->m_cond, &ctx->m_inside,
-                      &ctx->m_ll, &ctx->m_status, &ctx->m_in_theta, &ctx->m_in_logL, &ctx->m_out_theta, &ctx->m_out_logL, &ctx->row_map, &ctx->m_groups};
+                      &ctx->m_ll, &ctx->m_status, &ctx->m_in_theta, &ctx->m_in_logL, &ctx->m_out_theta, &ctx->m_out_logL, &ctx->row_map, &ctx->m_groups, &ctx->logL_scratch};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->d_cond) cudaFree(ctx->d_cond);
@@ -487,6 +520,20 @@ int hmx_synchronize(hmx_ctx* ctx) {
 int hmx_loglik_batch(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, int64_t N, double* logL,
                      double* obs_state, uint32_t* status, uint32_t* newton_iters) {
     return batch_impl(ctx, theta, cond_id, N, logL, obs_state, status, newton_iters, nullptr);
+}
+
+int hmx_tsm_obs_rows(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, int64_t N, double* x0, double* sigma2,
+                     double* x1, double* logL, uint32_t* status) {
+    if (!ctx) return HMX_ERR_INVALID;
+    if (N > 0 && !sigma2 && !x1 && !x0) return fail(ctx, HMX_ERR_INVALID, "hmx_tsm_obs_rows: no output requested");
+    CU(cudaSetDevice(ctx->device));
+    double* ll = logL;
+    if (!ll && N > 0) {  // the observation kernel always writes the log-likelihood: give it context scratch
+        int rc = ensure(ctx, ctx->logL_scratch, (size_t)N * sizeof(double));
+        if (rc) return rc;
+        ll = (double*)ctx->logL_scratch.p;
+    }
+    return batch_impl(ctx, theta, cond_id, N, ll, x0, status, nullptr, nullptr, sigma2, x1);
 }
 
 int hmx_trajectory_batch(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, int64_t N, double* g,
@@ -878,8 +925,9 @@ int hmx_get_counters(hmx_ctx* ctx, hmx_counters* out) {
     CU(cudaMemcpy(h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
     if (ctx->timing_pending) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ode_ms = ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ode_ms = ctx->ode_ms_acc + ms;
         else cudaGetLastError();
+        ctx->ode_ms_acc = 0.0;
         ctx->timing_pending = false;
     }
     out->evals = ctx->last_evals;

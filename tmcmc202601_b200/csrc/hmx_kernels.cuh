@@ -252,6 +252,8 @@ struct ObsParams {
     double* logL;
     double* obs_state;     // [N, n_obs_max, 12] or null
     long long obs_stride;  // n_obs_max * 12
+    double* sigma2;        // [N, n_obs_max, 12] or null: TSM variance at the observation rows (S4:1146-1149)
+    double* x1;            // [N, n_obs_max, 12, 20] or null: local sensitivities at the observation rows (S4:1150)
     int n_cond;
 };
 
@@ -266,7 +268,9 @@ __global__ void __launch_bounds__(128) obs_kernel(const __grid_constant__ ObsPar
     for (int k = 0; k < HMX_NTHETA; ++k) th[k] = __ldg(P.theta + w * HMX_NTHETA + k);
     uint32_t st = 0u;
     const double ll = obs_loglik<ALPHA, HILL>(P.K, C, P.TM, th, P.pairs + w * P.pair_stride, P.status_in[w],
-                                              P.obs_state ? P.obs_state + w * P.obs_stride : nullptr, &st);
+                                              P.obs_state ? P.obs_state + w * P.obs_stride : nullptr, &st,
+                                              P.sigma2 ? P.sigma2 + w * P.obs_stride : nullptr,
+                                              P.x1 ? P.x1 + w * P.obs_stride * HMX_NTHETA : nullptr);
     P.logL[w] = ll;
     if (P.status_out) P.status_out[w] = st;
 }

@@ -28,7 +28,8 @@ constexpr int kPairStride = 24;
 
 template <bool ALPHA, int HILL>
 HMX_HD double obs_loglik(const SolverConsts& K, const CondConsts& C, const ThetaMap& TM, const double* theta,
-                         const double* pairs, uint32_t solve_status, double* obs_state, uint32_t* status_out) {
+                         const double* pairs, uint32_t solve_status, double* obs_state, uint32_t* status_out,
+                         double* sig2_out = nullptr, double* x1_out = nullptr) {
     double A[15], b[5];
     theta_to_Ab(theta, A, b);
     bool bad = (solve_status & kStNonfinite) != 0u;
@@ -56,6 +57,9 @@ HMX_HD double obs_loglik(const SolverConsts& K, const CondConsts& C, const Theta
 #pragma unroll
         for (int i = 0; i < 5; ++i) covp[i] = 0.0;
 
+        if (x1_out) {  // _last_x1[idx] (S4:1150): column k = theta_k, zero where theta_k is not active
+            for (int i = 0; i < 12 * HMX_NTHETA; ++i) x1_out[(size_t)o * 12 * HMX_NTHETA + i] = 0.0;
+        }
         if (C.tsm_variance) {
             Eval e;
             residual<ALPHA, HILL>(K, x, gp, A, b, e);  // clipped copies, as compute_Jacobian_matrix does (S5:734-758)
@@ -89,6 +93,10 @@ HMX_HD double obs_loglik(const SolverConsts& K, const CondConsts& C, const Theta
                 }
                 double x1[12];
                 direction<ALPHA, HILL>(K, e, A, b, x1);
+                if (x1_out) {
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) x1_out[((size_t)o * 12 + i) * HMX_NTHETA + k] = x1[i];
+                }
 #pragma unroll
                 for (int i = 0; i < 12; ++i) sig2[i] = fma(x1[i] * x1[i], var_k, sig2[i]);
 #pragma unroll
@@ -102,6 +110,10 @@ HMX_HD double obs_loglik(const SolverConsts& K, const CondConsts& C, const Theta
                 sig2[i] += 1e-12;  // S4:324-332
                 if (!(fabs(sig2[i]) <= 1.79e308)) bad = true;
             }
+        }
+        if (sig2_out) {  // sigma2[idx] of solve_tsm (S4:1146-1149); zeros on the np.allclose short-cut (TSMA:366-401)
+#pragma unroll
+            for (int i = 0; i < 12; ++i) sig2_out[(size_t)o * 12 + i] = sig2[i];
         }
 
         // EV:679-745 then EV:305-334 for this row
