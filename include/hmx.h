@@ -52,6 +52,8 @@ typedef enum {
 #define HMX_ST_NONFINITE 1u /* trajectory / likelihood inputs non-finite -> logL = -1e20 (EV:657-667,747-753) */
 #define HMX_ST_MAXITER 2u   /* a time step exhausted max_newton_iter (S5:308) */
 #define HMX_ST_SINGULAR 4u  /* a Newton direction came out non-finite (the reference's LinAlgError/ridge path, S5:369-373) */
+#define HMX_ST_BAD_COND 8u  /* cond_id outside [0, n_cond) in a DEVICE array -> logL = -1e20 (a host array is rejected with
+                               HMX_ERR_INVALID before anything runs) */
 
 /* One experimental condition: what LogLikelihoodEvaluator.__init__ receives (EV:381-398) plus the
  * per-condition initial state from the loader (MAIN:1907-1928). */
@@ -114,6 +116,18 @@ int hmx_abi_version(void);
  *   newton_iters [N] quasi-Newton iterations summed over the time steps, or NULL */
 int hmx_loglik_batch(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, int64_t N,
                      double* logL, double* obs_state, uint32_t* status, uint32_t* newton_iters);
+
+/* replaces: BiofilmTSM.solve_tsm (S4:1077-1160) as the evaluator consumes it (EV:645-745), i.e. at the rows idx_sparse:
+ *   x0     [N,n_obs_max,12]     = x0[idx_sparse]          (the deterministic trajectory rows), or NULL
+ *   sigma2 [N,n_obs_max,12]     = sig2[idx_sparse]        (S4:1143-1149: sum_k x1_k^2 (cov_rel theta_k)^2 + 1e-12), or NULL
+ *   x1     [N,n_obs_max,12,20]  = tsm._last_x1[idx_sparse] (S4:1150) with one column per theta_k (zero where k is not in
+ *                                 active_idx; the reference stores only the active columns, in active_idx order), or NULL
+ *   logL   [N] or NULL, status [N] or NULL as in hmx_loglik_batch.
+ * The local sensitivity x1[t,:,k] = solve(J(g_t, g_{t-1}), -dQ/dtheta_k) depends on (g_t, g_{t-1}) only, which is why the
+ * observation rows suffice.  idx_sparse = 0 returns the row-1 sensitivities (S4:1139-1141).  Conditions with
+ * tsm_variance = 0 (the np.allclose short-cut, TSMA:366-401) return zeros. */
+int hmx_tsm_obs_rows(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, int64_t N, double* x0, double* sigma2,
+                     double* x1, double* logL, uint32_t* status);
 
 /* replaces: BiofilmNewtonSolver5S.run_deterministic / .solve (S5:561-581, 646) for a batch.
  *   g [N,n_steps+1,12] row-major;  t_arr is (arange(n_steps+1) * dt) and is left to the caller. */

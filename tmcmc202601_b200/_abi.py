@@ -21,6 +21,7 @@ MAX_COND = 8
 ST_NONFINITE = 1
 ST_MAXITER = 2
 ST_SINGULAR = 4
+ST_BAD_COND = 8
 
 LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libhamilton.so"
 
@@ -147,6 +148,7 @@ EXPORTS = [
     "hmx_set_timing",
     "hmx_measure_fp64_peak",
     "hmx_mutate", "hmx_mutate_groups", "hmx_trajectory_rows", "hmx_set_latency_kernel", "hmx_cumsum",
+    "hmx_tsm_obs_rows",
 ]
 
 
@@ -278,6 +280,7 @@ def load() -> C.CDLL:
     # array arguments are raw addresses (host or device), hence c_void_p everywhere
     lib.hmx_loglik_batch.argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp, vp]
     lib.hmx_trajectory_batch.argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp]
+    lib.hmx_tsm_obs_rows.argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp]
     lib.hmx_trajectory_rows.argtypes = [vp, vp, vp, C.c_int64, vp, C.c_int32, vp, vp, vp]
     lib.hmx_beta_step.argtypes = [vp, vp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp]
     lib.hmx_weights.argtypes = [vp, vp, C.c_int64, C.c_double, vp, vp]

@@ -30,11 +30,17 @@ namespace hmx {
 constexpr int kOdeThreads = HMX_ODE_THREADS;      // 4 warps: one per SM sub-partition
 constexpr int kOdeMinBlocks = HMX_ODE_MINBLOCKS;  // 2 -> 255 registers / thread available, 8 warps / SM
 
-// cond_id values outside [0, n_cond) are treated as condition 0 (the C ABI documents the valid range)
+// A host cond_id array is validated by the API (HMX_ERR_INVALID).  A device array cannot be checked without a
+// synchronisation, so the kernels do it: the solve runs as condition 0 (the lane needs some valid work) and the
+// observation kernel then returns logL = -1e20 with HMX_ST_BAD_COND set for that evaluation.
 __device__ __forceinline__ int cond_index(const int32_t* cond_id, long long i, int n_cond) {
     const int c = cond_id ? cond_id[i] : 0;
     return ((unsigned)c < (unsigned)n_cond) ? c : 0;
 }
+__device__ __forceinline__ bool cond_valid(const int32_t* cond_id, long long i, int n_cond) {
+    return !cond_id || ((unsigned)cond_id[i] < (unsigned)n_cond);
+}
+constexpr uint32_t kStBadCond = 8u;  // == HMX_ST_BAD_COND
 
 struct OdeCond {
     double g0[12];
@@ -271,8 +277,9 @@ __global__ void __launch_bounds__(128) obs_kernel(const __grid_constant__ ObsPar
                                               P.obs_state ? P.obs_state + w * P.obs_stride : nullptr, &st,
                                               P.sigma2 ? P.sigma2 + w * P.obs_stride : nullptr,
                                               P.x1 ? P.x1 + w * P.obs_stride * HMX_NTHETA : nullptr);
-    P.logL[w] = ll;
-    if (P.status_out) P.status_out[w] = st;
+    const bool okc = cond_valid(P.cond_id, w, P.n_cond);
+    P.logL[w] = okc ? ll : -1e20;
+    if (P.status_out) P.status_out[w] = okc ? st : (st | kStBadCond);
 }
 
 // ---- FP64 peak: 8 independent DFMA chains per thread, operands in registers ---------------------------

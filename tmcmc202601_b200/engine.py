@@ -105,6 +105,23 @@ class HamiltonEngine:
             "hmx_loglik_batch",
         )
 
+    def tsm_obs_rows(self, theta, cond_id=None, want_x1=True):
+        """BiofilmTSM.solve_tsm at the observation rows (hmx_tsm_obs_rows): returns x0[N,n_obs,12], sigma2[N,n_obs,12],
+        x1[N,n_obs,12,20] (or None), logL[N], status[N]."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        if theta.ndim != 2 or theta.shape[1] != _abi.NTHETA:
+            raise ValueError("theta must have shape (N, 20)")
+        N = theta.shape[0]
+        cid = None if cond_id is None else np.ascontiguousarray(cond_id, dtype=np.int32)
+        x0 = np.zeros((N, self.n_obs_max, _abi.NSTATE))
+        sig2 = np.zeros((N, self.n_obs_max, _abi.NSTATE))
+        x1 = np.zeros((N, self.n_obs_max, _abi.NSTATE, _abi.NTHETA)) if want_x1 else None
+        logL = np.empty(N)
+        status = np.zeros(N, dtype=np.uint32)
+        self._check(self._lib.hmx_tsm_obs_rows(self._ctx, _addr(theta), _addr(cid), N, _addr(x0), _addr(sig2), _addr(x1), _addr(logL),
+                                               _addr(status)), "hmx_tsm_obs_rows")
+        return x0, sig2, x1, logL, status
+
     def trajectory_batch(self, theta, cond_id=None):
         """g[N, n_steps+1, 12] (hmx_trajectory_batch)."""
         theta = np.ascontiguousarray(theta, dtype=np.float64)
