@@ -20,8 +20,12 @@ A "step" is one pass of the hot path over one batch:
 `e2e`    : the same step through the public host-facing API (NumPy buffers: theta/cond_id H2D and
            logL/weights/indices/covariance D2H inside the timed region).
 `roofline`: FP64 FMA pipe (the path is compute bound; HBM traffic is ~1.2 KB per 2e7-flop evaluation).
-`cpu_baseline` / `--impl reference`: the oracle's C restatement of the reference algorithm (kind "port": the
-           reference itself is Python+numba and its tree does not travel to the GPU box) on all host threads.
+`cpu_baseline` / `--impl reference`: the reference AS SHIPPED (kind "reference": oracle/_ref, a build-time snapshot of the
+           reference's own evaluator modules written by oracle/make_ref.py, driven through its public API
+           LogLikelihoodEvaluator + evaluate_particles_parallel on all host cores); when oracle/_ref is absent, the oracle's C
+           restatement (kind "port") on all host threads.  The port's number is always reported next to it.
+`sweep`, `t500`, `tmcmc_runs`: (N = 1, after the timed regions) the rest of BASELINE.json: the 10^4-10^7 per-condition sweep,
+           the 500-step configuration, configs[0]/[1]/[2] wall times and a configs[3] Hill-sweep run.  --quick skips them.
 `tmcmc_run`: (N = 1, after the timed regions) the other half of BASELINE.json's metric, "TMCMC wall time per run": configs[1]
            through the reference-shaped API, host-side and device-side mutation, posterior checked against the stored
            reference run (226 865 s there).  --no-tmcmc-run skips it.
@@ -60,6 +64,7 @@ FLOPS_PER_DIRECTION = 850.0
 # DRAM bytes per evaluation of the same capture (dram__bytes_read.sum + dram__bytes_write.sum) / 262144
 DRAM_BYTES_PER_EVAL_NCU = 1041  # dram__bytes_read.sum + dram__bytes_write.sum of ode_kernel per evaluation, ncu --set full (profiles/r01j_ode_kernel_rebased.json: 59.5 + 213.3 MB for 262 144 evaluations)
 # the reference-equivalent count of SURVEY.md section 8(d): dense Q + K + dgesv per iteration, Q per extra trial
+FP64_NOMINAL_TFLOPS = 37.2  # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
 REF_FLOPS_PER_ITER = 2778.0
 REF_FLOPS_PER_TRIAL = 384.0
 
@@ -121,6 +126,27 @@ def synth_batch(rank: int):
     return wl
 
 
+def reference_as_shipped(wl, n_cond_sample: int = 1) -> dict | None:
+    """The reference's own evaluator (oracle/_ref) on a bounded sample: `cores` evaluations of the LAST condition(s) of the
+    workload through core.tmcmc.evaluate_particles_parallel, after one warm-up call (numba JIT) in this process."""
+    from oracle import ref_runner
+
+    if not ref_runner.available():
+        return None
+    cores = os.cpu_count() or 1
+    arm = ref_runner.ReferenceArm(wl.config, n_jobs=cores)
+    conds = list(range(N_COND))[-n_cond_sample:]
+    sel = np.concatenate([np.nonzero(wl.cond_id == c)[0][:cores] for c in conds])
+    warm = np.concatenate([np.nonzero(wl.cond_id == c)[0][cores:cores + 1] for c in conds])
+    t_warm = arm.warm_up(wl.theta[warm], wl.cond_id[warm])
+    t0 = time.perf_counter()
+    arm.evaluate(wl.theta[sel], wl.cond_id[sel])
+    dt = time.perf_counter() - t0
+    return {"value": sel.size / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"{sel.size} evaluations (condition(s) {conds}) through the reference's LogLikelihoodEvaluator + "
+                      f"evaluate_particles_parallel(n_jobs={cores}) from oracle/_ref, {dt:.1f} s after a {t_warm:.1f} s warm-up (numba JIT)"}
+
+
 def cpu_baseline(wl, budget_s: float = 12.0, max_evals: int = 16384) -> dict:
     """The oracle port on all host threads, on a bounded prefix-sample of the same workload (equal share per condition)."""
     from oracle import oracle as orc
@@ -143,23 +169,47 @@ def cpu_baseline(wl, budget_s: float = 12.0, max_evals: int = 16384) -> dict:
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; the Python+numba original does not travel) on the host."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores.  oracle/_ref (the reference as
+    shipped, kind "reference") when the build-time snapshot is present, else the oracle's C restatement (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     wl = synth_batch(0)
     from oracle import oracle as orc
+    from oracle import ref_runner
 
     cores = os.cpu_count() or 1
-    per_step = max(cores * 64, 256)  # evaluations per step: a bounded sample, ~2-3 s of CPU work per step
-    sel_all = np.concatenate([np.nonzero(wl.cond_id == c)[0][: (args.steps + args.warmup) * per_step // N_COND + per_step] for c in range(N_COND)])
-    rng = np.random.default_rng(0)
-    rng.shuffle(sel_all)
+    n_total = args.steps + args.warmup
+    if ref_runner.available() and os.environ.get("HMX_BENCH_REF_KIND", "reference") != "port":
+        # one step = `cores` evaluations of ONE condition (step s -> condition s mod 4) through evaluate_particles_parallel:
+        # ~5.4 s of CPU per evaluation per core, so a step costs ~6 s and all cores are busy
+        kind, per_step = "reference", cores
+        arm = ref_runner.ReferenceArm(wl.config, n_jobs=cores)
+        by_cond = [np.nonzero(wl.cond_id == c)[0] for c in range(N_COND)]
+        warm = np.array([ix[-1] for ix in by_cond])
+        arm.warm_up(wl.theta[warm], wl.cond_id[warm])  # numba JIT + first call per condition, untimed
+
+        def step_fn(s):
+            c = s % N_COND
+            sel = by_cond[c][(s // N_COND) * per_step:(s // N_COND + 1) * per_step]
+            arm.evaluate(wl.theta[sel], wl.cond_id[sel])
+
+        sample = (f"{per_step} evaluations per step (one condition per step, cycling) x {args.steps} steps through the reference's "
+                  f"LogLikelihoodEvaluator + evaluate_particles_parallel(n_jobs={cores}) from oracle/_ref")
+    else:
+        kind, per_step = "port", max(cores * 64, 256)  # ~2-3 s of CPU work per step
+        sel_all = np.concatenate([np.nonzero(wl.cond_id == c)[0][: n_total * per_step // N_COND + per_step] for c in range(N_COND)])
+        np.random.default_rng(0).shuffle(sel_all)
+
+        def step_fn(s):
+            sel = sel_all[s * per_step:(s + 1) * per_step]
+            orc.evaluate_hmx(wl.config, wl.theta[sel], wl.cond_id[sel], n_threads=cores)
+
+        sample = f"{per_step} evaluations per step x {args.steps} steps, oracle/hamilton_oracle.c on {cores} pthreads"
     times = []
-    for s in range(args.warmup + args.steps):
-        sel = sel_all[s * per_step:(s + 1) * per_step]
+    for s in range(n_total):
         t0 = time.perf_counter()
-        orc.evaluate_hmx(wl.config, wl.theta[sel], wl.cond_id[sel], n_threads=cores)
+        step_fn(s)
         dt = time.perf_counter() - t0
         if s >= args.warmup:
             times.append(dt)
@@ -170,8 +220,7 @@ def run_reference_arm(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.gpus, per_step_note=f"each step = a bounded sample of {per_step} evaluations of the same workload"),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{per_step} evaluations per step x {len(times)} steps, oracle/hamilton_oracle.c on {cores} pthreads"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -215,6 +264,175 @@ def tmcmc_run():
     return out
 
 
+def timed_pass(eng, th_d, cid_d, ll_d, reps: int, local_rank: int) -> dict:
+    """`reps` passes of the hot path (ODE + likelihood kernels) over a device-resident batch, CUDA events, clocks sampled."""
+    import torch
+
+    eng.loglik_batch_device(th_d, cid_d, ll_d)  # warm-up (buffer growth, cost-ordered work list)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        eng.loglik_batch_device(th_d, cid_d, ll_d)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    n = th_d.shape[0]
+    c = eng.counters()
+    return {"evals": int(n), "reps": reps, "ms_per_pass": ms, "evals_per_s": n / (ms * 1e-3), "newton_iters_per_eval": c["newton_iters"] / n,
+            "nonfinite": int((ll_d == -1e20).sum().item()), "clocks": sampler.stop()}
+
+
+def device_prior_batch(keys, n_per_cond: int, dev, seed: int):
+    """theta ~ U(prior bounds of condition c) drawn ON the device (torch Philox): 10^7 x 4 x 20 doubles are 6.4 GB, and host RNG
+    output is not the thing measured.  Locked parameters (bounds (0,0)) stay 0, as in workloads.four_condition_workload."""
+    import torch
+
+    from tmcmc202601_b200 import workloads
+
+    conds = workloads.load_conditions()
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    th = torch.empty((len(keys) * n_per_cond, 20), dtype=torch.float64, device=dev)
+    cid = torch.empty(len(keys) * n_per_cond, dtype=torch.int32, device=dev)
+    for c, k in enumerate(keys):
+        b = torch.tensor(conds[k]["bounds"], dtype=torch.float64, device=dev)
+        blk = th[c * n_per_cond:(c + 1) * n_per_cond]
+        blk.uniform_(0.0, 1.0, generator=g)
+        blk.mul_(b[:, 1] - b[:, 0]).add_(b[:, 0])
+        cid[c * n_per_cond:(c + 1) * n_per_cond] = c
+    return th, cid
+
+
+def throughput_sweep(eng, dev, local_rank: int, sizes=(10**4, 10**5, 10**6, 10**7)) -> list:
+    """BASELINE.json configs[4] in full: N in {1e4, 1e5, 1e6, 1e7} theta per condition x 4 conditions on one GPU (the largest
+    size runs in ten 4 Mi-evaluation chunks inside hmx_loglik_batch)."""
+    import torch
+
+    from tmcmc202601_b200 import workloads
+
+    out = []
+    for n in sizes:
+        try:
+            th, cid = device_prior_batch(workloads.CONDITION_KEYS, n, dev, seed=20260101 + n % 9973)
+            ll = torch.empty(th.shape[0], dtype=torch.float64, device=dev)
+            r = timed_pass(eng, th, cid, ll, reps=3 if n <= 10**5 else 1, local_rank=local_rank)
+            r["n_per_condition"] = n
+            out.append(r)
+            del th, cid, ll
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001 - a side measurement must not lose the headline line
+            out.append({"n_per_condition": n, "error": f"{type(e).__name__}: {e}"})
+    return out
+
+
+def t500_pass(dev, local_rank: int) -> dict:
+    """The 500-step configuration of deeponet/surrogate_tmcmc.py:353-365 (dt=1e-5, c=alpha=100, phi_init=0.2, K_hill=0.05,
+    n_hill=4) on the same 4 x 262144 prior batch: the configuration for which 10^7 evaluations/s on 8 GPUs is reachable."""
+    import torch
+
+    from tmcmc202601_b200 import workloads
+    from tmcmc202601_b200.engine import HamiltonEngine
+
+    try:
+        solver = dict(workloads.T500_SOLVER, K_hill=0.05, n_hill=4.0)
+        wl0 = workloads.four_condition_workload(8, solver=solver)
+        for k in range(N_COND):  # observation days rescaled onto the 500-step grid, phi_init of the surrogate set-up
+            for o, r in enumerate((68, 136, 226, 339, 475)):
+                wl0.config.cond[k].idx_sparse[o] = r
+            for i in range(5):
+                wl0.config.cond[k].phi_init[i] = 0.2
+        eng = HamiltonEngine(wl0.config, device=local_rank)
+        eng.use_torch_stream()
+        th, cid = device_prior_batch(workloads.CONDITION_KEYS, N_PER_COND, dev, seed=500)
+        ll = torch.empty(th.shape[0], dtype=torch.float64, device=dev)
+        r = timed_pass(eng, th, cid, ll, reps=3, local_rank=local_rank)
+        eng.close()
+        r["config"] = "dt=1e-5 x 500 steps, c=alpha=100, phi_init=0.2, K_hill=0.05 n_hill=4, 4 x 262144 prior draws"
+        return r
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
+def tmcmc_runs(local_rank: int) -> dict:
+    """Wall time per TMCMC run for BASELINE.json configs[0], [2] and [3] (configs[1] is `tmcmc_run`), through the reference-shaped
+    API.  No stored reference posterior exists for these (the reference needs ~60 h per run), so the posterior check is the
+    agreement of the two independent RNG paths: host-side mutation (the reference's NumPy stream) vs device-side (Philox)."""
+    sys.path.insert(0, str(ROOT / "scripts"))
+    import run_production_tmcmc as rp
+
+    from tmcmc202601_b200 import tmcmc, workloads
+    from tmcmc202601_b200.evaluator import LogLikelihoodEvaluator
+
+    out = {}
+
+    def z_between(a, b, n_eff=200.0):
+        return float(np.max(np.abs(a.mean(0) - b.mean(0)) / np.sqrt((a.std(0, ddof=1) ** 2 + b.std(0, ddof=1) ** 2) / n_eff + 1e-300)))
+
+    def clocked(fn):
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        r = fn()
+        return r, sampler.stop()
+
+    # configs[0]: Commensal Static, N = 1000, 2 chains
+    try:
+        (h, hs, _), ck = clocked(lambda: rp.run_condition("Commensal_Static", 1000, 2, device_mutation=False))
+        (d, ds, _), _ = clocked(lambda: rp.run_condition("Commensal_Static", 1000, 2, device_mutation=True))
+        act = workloads.load_conditions()["Commensal_Static"]["active_indices"]
+        out["configs0_commensal_static"] = {
+            "host_mutation_wall_s": h["wall_s"], "device_mutation_wall_s": d["wall_s"], "likelihood_evaluations": h["likelihood_evaluations"],
+            "stages": h["stages"], "converged": h["converged"], "logL_max": [h["logL_max"], d["logL_max"]],
+            "posterior_z_host_vs_device_max": z_between(hs[:, act], ds[:, act]), "clocks": ck}
+    except Exception as e:  # noqa: BLE001
+        out["configs0_commensal_static"] = {"error": f"{type(e).__name__}: {e}"}
+
+    # configs[2]: the four conditions x 2 chains x 1000 particles, launches merged across the eight chains
+    try:
+        (hm, ho), ck = clocked(lambda: rp.run_merged(workloads.CONDITION_KEYS, 1000, 2, device_mutation=False))
+        (dm, do), _ = clocked(lambda: rp.run_merged(workloads.CONDITION_KEYS, 1000, 2, device_mutation=True))
+        conds = workloads.load_conditions()
+        zs = []
+        for k, a, b in zip(workloads.CONDITION_KEYS, ho, do):
+            act = conds[k]["active_indices"]
+            zs.append(z_between(np.concatenate(a["chains"])[:, act], np.concatenate(b["chains"])[:, act]))
+        out["configs2_four_conditions"] = {
+            "host_mutation_wall_s": hm["wall_s"], "device_mutation_wall_s": dm["wall_s"], "merged_launches": dm["merged_launches"],
+            "likelihood_evaluations": dm["likelihood_evaluations"], "converged": [p["converged"] for p in dm["per_condition"]],
+            "posterior_z_host_vs_device_max": zs, "clocks": ck}
+    except Exception as e:  # noqa: BLE001
+        out["configs2_four_conditions"] = {"error": f"{type(e).__name__}: {e}"}
+
+    # configs[3]: Hill-gate sweep member K = 0.05, n = 4, N = 10^5 particles per stage, device-side mutation
+    try:
+        cd = workloads.load_conditions()["Dysbiotic_HOBIC"]
+        sk = dict(workloads.PRODUCTION_SOLVER, phi_init=cd["phi_init"], n_hill=4.0)
+        base = np.full(20, 1.5)
+        base[cd["locked"]] = 0.0
+
+        def run():
+            ev = LogLikelihoodEvaluator(sk, [0, 1, 2, 3, 4], cd["active_indices"], base, cd["data"], cd["idx_sparse"], cd["sigma_obs"],
+                                        cov_rel=0.005, theta_linearization=base, device=local_rank)
+            t0 = time.perf_counter()
+            res = tmcmc.run_TMCMC(ev, [tuple(b) for b in cd["bounds"]], n_particles=100000, n_stages=30, seed=4242, min_delta_beta=0.02,
+                                  max_delta_beta=0.5, evaluator=ev, theta_base_full=base, active_indices=cd["active_indices"],
+                                  n_mutation_steps=5, device_mutation=True)
+            wall = time.perf_counter() - t0
+            n = ev.health.n_calls
+            ev.close()
+            return res, wall, n
+
+        (res, wall, n), ck = clocked(run)
+        out["configs3_hill_n4_1e5"] = {"wall_s": wall, "stages": len(res.stage_summary), "s_per_stage": wall / max(len(res.stage_summary), 1),
+                                       "likelihood_evaluations": int(n), "evals_per_s_in_run": n / wall, "log_evidence": res.log_evidence,
+                                       "logL_max": float(res.logL_values.max()), "beta_final": res.beta_schedule[-1], "clocks": ck}
+    except Exception as e:  # noqa: BLE001
+        out["configs3_hill_n4_1e5"] = {"error": f"{type(e).__name__}: {e}"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -223,28 +441,43 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-tmcmc-run", action="store_true", help="skip the configs[1] TMCMC wall-time side measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline line only: no sweep / t500 / tmcmc side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
 
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = synth_batch(rank)
+    M = wl.theta.shape[0]
+
     import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback (use --impl reference for the CPU arm)")
+
+    # CPU baselines first (rank 0, N = 1), before this process creates a CUDA context: the reference forks worker processes
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        port = cpu_baseline(wl)
+        try:
+            shipped = reference_as_shipped(wl)
+        except Exception as e:  # noqa: BLE001
+            shipped = None
+            port["reference_as_shipped_error"] = f"{type(e).__name__}: {e}"
+        cpu = dict(shipped, port=port) if shipped else port
+
     import torch.distributed as dist
 
     from tmcmc202601_b200.engine import HamiltonEngine
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
-    wl = synth_batch(rank)
-    M = wl.theta.shape[0]
     eng = HamiltonEngine(wl.config, device=local_rank)
     eng.use_torch_stream()
     fp64_peak = eng.measure_fp64_peak()
@@ -322,11 +555,15 @@ def main():
     value = world * M * args.steps / (elapsed_ms * 1e-3)
 
     # ---- end to end through the host-facing API ---------------------------------------------------------
+    # The particle matrix is uploaded ONCE per step into a context-owned device array (hmx_population_*) and every call of the
+    # step reads it there; everything else (cond_id, log-likelihoods, weights, indices, moments) crosses the bus as NumPy.
     th_h = torch.from_numpy(wl.theta).pin_memory().numpy()
     cid_h = torch.from_numpy(wl.cond_id).pin_memory().numpy()
+    th_pop = eng.device_array((M, 20))
 
     def host_step(step: int):
-        logL = eng.loglik_batch(th_h, cid_h)  # H2D theta + cond_id, D2H logL
+        th_pop.upload(th_h)                      # H2D theta (pinned source)
+        logL = eng.loglik_batch(th_pop, cid_h)   # H2D cond_id, D2H logL
         if world > 1:
             g = torch.from_numpy(logL).to(dev)
             dist.all_gather_into_tensor(ll_all, g)
@@ -341,12 +578,12 @@ def main():
             idx = eng.resample(w, float(u_draw[(step * N_COND + c) % 1024]))
             lo = c * N_PER_COND
             w_loc = w[rank * N_PER_COND:(rank + 1) * N_PER_COND]
-            mom = eng.weighted_moments(th_h[lo:lo + N_PER_COND], w_loc)
+            mom = eng.weighted_moments(th_pop[lo:lo + N_PER_COND], w_loc)
             if world > 1:
                 mt = torch.from_numpy(mom).to(dev)
                 dist.all_reduce(mt)
                 mom = mt.cpu().numpy()
-            sc = eng.weighted_scatter(th_h[lo:lo + N_PER_COND], w_loc, mom[2:] / mom[0])
+            sc = eng.weighted_scatter(th_pop[lo:lo + N_PER_COND], w_loc, mom[2:] / mom[0])
             if world > 1:
                 st = torch.from_numpy(sc).to(dev)
                 dist.all_reduce(st)
@@ -358,7 +595,7 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    e2e_steps = max(2, min(args.steps, 4))
+    e2e_steps = args.steps
     for s in range(e2e_steps):
         host_step(1 + s)
     e1.record()
@@ -369,10 +606,10 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * M * e2e_steps / (float(te.item()) * 1e-3)
     pop_n = world * N_PER_COND
-    # bytes the host-facing calls copy per step: theta + cond_id in, logL out; per condition the population logL
-    # (beta_step, weights), w (resample), theta_c + w_c twice (moments, scatter) and the mean in; w, idx, 3 scalars,
-    # 22 moments and the 20x20 scatter out
-    h2d = M * (20 * 8 + 4) + N_COND * (3 * pop_n * 8 + 2 * N_PER_COND * (20 * 8 + 8) + 20 * 8)
+    # bytes the host-facing calls copy per step: theta (once) + cond_id in, logL out; per condition the population logL
+    # (beta_step, weights), w (resample), w_c twice (moments, scatter) and the mean in; w, idx, 3 scalars, 22 moments and
+    # the 20x20 scatter out
+    h2d = M * (20 * 8 + 4) + N_COND * (3 * pop_n * 8 + 2 * N_PER_COND * 8 + 20 * 8)
     d2h = M * 8 + N_COND * (2 * pop_n * 8 + 3 * 8 + 22 * 8 + 400 * 8)
 
     # ---- roofline of the dominant kernel (ode_kernel): executed FP64 flops / CUDA-event duration ---------
@@ -385,9 +622,10 @@ def main():
     roofline = {
         "bound": "fp64", "kernel": "hmx::ode_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
         "frac": achieved / fp64_peak if fp64_peak > 0 else None,
-        "traffic": DRAM_BYTES_PER_EVAL_NCU * M,  # bytes per launch; ncu measured 1041 B/evaluation, algorithmic 1144
+        "frac_of_nominal_peak": achieved / FP64_NOMINAL_TFLOPS,
+        "traffic": DRAM_BYTES_PER_EVAL_NCU * M,  # bytes per launch; ncu measured per evaluation, algorithmic 1144
         "peak_source": "measured live by hmx_measure_fp64_peak (register-resident DFMA loop); MEASURED_PEAKS.json has no FP64 entry "
-                       "(nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2)",
+                       f"(nominal 148 SM x 64 FMA x 2 x 1.965 GHz = {FP64_NOMINAL_TFLOPS}: frac_of_nominal_peak)",
         "kernel_ms_per_launch": ode_avg_ms, "kernel_share_of_step": ode_avg_ms * args.steps / elapsed_ms,
         "flops_per_launch": flops_per_launch, "newton_iters_per_eval": iters_sum / (M * args.steps),
         "residual_evals_per_eval": trips_sum / (M * args.steps),
@@ -408,10 +646,14 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(wl)
-        if world == 1 and not args.no_tmcmc_run:
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if world == 1 and not args.quick:
+            line["sweep"] = throughput_sweep(eng, dev, local_rank)
+            line["t500"] = t500_pass(dev, local_rank)
+        if world == 1 and not args.no_tmcmc_run and not args.quick:
             line["tmcmc_run"] = tmcmc_run()
+            line["tmcmc_runs"] = tmcmc_runs(local_rank)
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

@@ -98,10 +98,24 @@ int hmx_create(hmx_ctx** ctx, const hmx_config* cfg, int32_t device);
 void hmx_destroy(hmx_ctx* ctx);
 /* message of the last failing call on ctx (ctx may be NULL: last hmx_create failure) */
 const char* hmx_last_error(const hmx_ctx* ctx);
-/* run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); NULL = context stream */
+/* run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); NULL = the context's own (non-blocking)
+ * stream.  The legacy default stream has handle 0: name it with cudaStreamLegacy ((cudaStream_t)0x1) -- work enqueued on
+ * the context's own stream is NOT ordered with work on the default stream. */
 int hmx_set_stream(hmx_ctx* ctx, void* cuda_stream);
 int hmx_synchronize(hmx_ctx* ctx);
 int hmx_abi_version(void);
+
+/* ---- device-resident arrays ("populations") --------------------------------------------------------
+ * Every array argument of this API may be a device pointer.  A caller without a CUDA binding of its own (the
+ * reference is NumPy-only) gets device arrays from the context: upload the particle matrix ONCE per stage and pass
+ * the returned pointer (or pointer + offset: plain row-major doubles) to hmx_loglik_batch, hmx_weighted_cov /
+ * _moments / _scatter and hmx_mutate instead of re-sending the host copy with every call.  Arrays are freed by
+ * hmx_population_destroy or with the context.  upload is asynchronous on the context stream (the source must stay
+ * valid until the next synchronising call; pass pinned memory for full PCIe rate), download synchronises. */
+int hmx_population_create(hmx_ctx* ctx, int64_t n_rows, int32_t n_cols, double** dev);
+int hmx_population_destroy(hmx_ctx* ctx, double* dev);
+int hmx_population_upload(hmx_ctx* ctx, double* dev, const double* host, int64_t n_values);
+int hmx_population_download(hmx_ctx* ctx, double* host, const double* dev, int64_t n_values);
 
 /* ---- the hot path -------------------------------------------------------------------------------- */
 /* replaces: evaluate_particles_parallel(LogLikelihoodEvaluator, theta) (TM:247-312) for FULL 20-vectors:
@@ -138,6 +152,33 @@ int hmx_trajectory_batch(hmx_ctx* ctx, const double* theta, const int32_t* cond_
  * set of deeponet/generate_training_data.py:283-289 (np.linspace(0, T, n_time_out, dtype=int)). */
 int hmx_trajectory_rows(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, int64_t N, const int32_t* rows,
                         int32_t n_rows, double* g, uint32_t* status, uint32_t* newton_iters);
+
+/* ---- legacy 4-species solver -------------------------------------------------------------------
+ * replaces: BiofilmNewtonSolver(**kw).run_deterministic(theta) of tmcmc/program2602/improved1207_paper_jit.py
+ * (S4:715-1053; numba integrator S4:610-700) for a batch: state g (10) = [phi1..4, phi0, psi1..4, gamma], theta (14) =
+ * a11,a12,a22,b1,b2, a33,a34,a44,b3,b4, a13,a14,a23,a24; inactive species are locked to phi = psi = 0 (S4:92-113).
+ * alpha_schedule (S4:783-822) arrives resolved to one switch level on the time grid: the step that produces time level n
+ * uses alpha_after when n >= alpha_switch_level, alpha_before otherwise (alpha_switch_level < 0: alpha_const throughout,
+ * which is what the reference's numba path does with any schedule, S4:1024; the reference honours the schedule only in its
+ * pure-Python fallback, S4:895-913).  n_species = 5 runs the same generic code on the 5-species model without the Hill
+ * gate (theta [N,20], state 12): a cross-check of this code path against hmx_trajectory_batch.
+ *   theta [N, 14 | 20];  rows: n_rows strictly ascending time levels in [0, n_steps] (host array), or NULL = all levels;
+ *   g [N, n_rows | n_steps + 1, 10 | 12];  status / newton_iters [N] or NULL.  The solver settings travel with the call;
+ *   the context supplies the device, the stream and scratch memory. */
+typedef struct {
+    int32_t n_species;           /* 4 (S4) or 5 (cross-check) */
+    double dt;
+    int32_t n_steps;
+    double eps, Kp1, c_const, alpha_const;
+    int32_t max_newton_iter;     /* the reference's numba loop hard-codes 50 (S4:685) */
+    double eta[5], eta_phi[5];
+    double phi_init[5];          /* the 4-species solver takes a scalar (S4:761): broadcast it */
+    int32_t active_species_mask; /* bit i <=> species i active */
+    int32_t alpha_switch_level;
+    double alpha_before, alpha_after;
+} hmx_legacy_config;
+int hmx_legacy_trajectory_rows(hmx_ctx* ctx, const hmx_legacy_config* cfg, const double* theta, int64_t N, const int32_t* rows,
+                               int32_t n_rows, double* g, uint32_t* status, uint32_t* newton_iters);
 
 /* ---- per-stage TMCMC arithmetic ------------------------------------------------------------------ */
 /* replaces: the 25-step ESS bisection for delta-beta (TM:613-659, beta_schedule="ess"). ess_at_lo is NaN

@@ -127,6 +127,29 @@ void orc_resample(const double* w, int64_t N, double u, int64_t* idx);
 void orc_weighted_cov(const double* theta, const double* w, int64_t N, int d, double* mean,
                       double* cov);
 
+/* ---- legacy 4-species solver (S4 = improved1207_paper_jit.py, class BiofilmNewtonSolver): hamilton_oracle4.c ---- */
+typedef struct {
+    double dt;
+    int32_t n_steps;
+    double eps, Kp1, c_const, alpha_const;
+    int32_t max_newton_iter; /* the numba time loop hard-codes 50 (S4:685) */
+    double eta[4], eta_phi[4];
+    double phi_init;      /* scalar in the 4-species solver (S4:761) */
+    int32_t active_mask;  /* bit i => species i active; inactive species are locked to phi = psi = 0 (S4:92-113) */
+    int32_t alpha_switch_level; /* < 0: alpha_const throughout; else time level n uses alpha_after when n >= this (S4:783-822) */
+    double alpha_before, alpha_after;
+} orc4_cfg;
+void orc4_theta_to_matrices(const double* theta /*[14]*/, double* A /*[16]*/, double* b /*[4]*/);
+void orc4_compute_Q(double* phi, double phi0, double* psi, double gamma, const double* phi_old, double phi0_old,
+                    const double* psi_old, const orc4_cfg* cfg, double alpha, const double* A, const double* b, double* Q /*[10]*/);
+void orc4_compute_J(double* phi, double phi0, double* psi, const double* phi_old, const double* psi_old, const orc4_cfg* cfg,
+                    double alpha, const double* A, const double* b, double* K /*[100]*/);
+int orc4_newton_step(const double* g_prev, const orc4_cfg* cfg, double alpha, const double* A, const double* b, double eps_tol,
+                     double* g_new, int64_t* n_trials, uint32_t* status);
+/* S4:610-700: g_arr [(n_steps+1), 10] row-major */
+void orc4_run_deterministic(const orc4_cfg* cfg, const double* theta, double* g_arr, int64_t* n_iters, int64_t* n_trials,
+                            uint32_t* status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,8 +59,8 @@ class CondCfg(C.Structure):
 
 def build(force: bool = False) -> Path:
     """Compile the oracle with the committed Makefile (gcc only; a couple of seconds)."""
-    src = _HERE / "hamilton_oracle.c"
-    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+    srcs = [_HERE / "hamilton_oracle.c", _HERE / "hamilton_oracle4.c", _HERE / "hamilton_oracle.h"]
+    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < max(p.stat().st_mtime for p in srcs):
         subprocess.run(["make", "-C", str(_HERE)], check=True, capture_output=True)
     return _LIB_PATH
 
@@ -287,6 +287,71 @@ def weighted_cov(theta, w):
     mean, cov = np.empty(d), np.empty((d, d))
     lib().orc_weighted_cov(_dptr(theta), _dptr(w), C.c_int64(N), C.c_int(d), _dptr(mean), _dptr(cov))
     return mean, cov
+
+
+# ---- legacy 4-species solver (hamilton_oracle4.c) ------------------------------------------------------------------
+class Cfg4(C.Structure):
+    _fields_ = [
+        ("dt", C.c_double), ("n_steps", C.c_int32), ("eps", C.c_double), ("Kp1", C.c_double), ("c_const", C.c_double),
+        ("alpha_const", C.c_double), ("max_newton_iter", C.c_int32), ("eta", C.c_double * 4), ("eta_phi", C.c_double * 4),
+        ("phi_init", C.c_double), ("active_mask", C.c_int32), ("alpha_switch_level", C.c_int32),
+        ("alpha_before", C.c_double), ("alpha_after", C.c_double),
+    ]
+
+
+def make_cfg4(dt=1e-5, maxtimestep=500, eps=1e-6, Kp1=1e-4, eta_vec=None, eta_phi_vec=None, c_const=100.0, alpha_const=100.0,
+              phi_init=0.2, active_species=None, max_newton_iter=50, alpha_switch_level=-1, alpha_before=None, alpha_after=None) -> Cfg4:
+    """Keyword names of BiofilmNewtonSolver.__init__ (S4:737-781); the schedule already resolved to a switch level."""
+    c = Cfg4()
+    c.dt, c.n_steps, c.eps, c.Kp1 = float(dt), int(maxtimestep), float(eps), float(Kp1)
+    c.c_const, c.alpha_const, c.max_newton_iter = float(c_const), float(alpha_const), int(max_newton_iter)
+    eta = np.ones(4) if eta_vec is None else _f64(eta_vec)
+    etaphi = np.ones(4) if eta_phi_vec is None else _f64(eta_phi_vec)
+    for i in range(4):
+        c.eta[i], c.eta_phi[i] = eta[i], etaphi[i]
+    c.phi_init = float(phi_init)
+    act = [0, 1, 2, 3] if active_species is None else list(active_species)
+    c.active_mask = sum(1 << i for i in act if 0 <= i < 4)
+    c.alpha_switch_level = int(alpha_switch_level)
+    c.alpha_before = float(alpha_const if alpha_before is None else alpha_before)
+    c.alpha_after = float(alpha_const if alpha_after is None else alpha_after)
+    return c
+
+
+def run_deterministic4(cfg: Cfg4, theta):
+    """-> (t_arr[T+1], g_arr[T+1,10], n_iters, n_trials, status); S4:1005-1028."""
+    theta = _f64(theta)
+    T = cfg.n_steps
+    g = np.empty((T + 1, 10))
+    its, tr, st = C.c_int64(0), C.c_int64(0), C.c_uint32(0)
+    lib().orc4_run_deterministic(C.byref(cfg), _dptr(theta), _dptr(g), C.byref(its), C.byref(tr), C.byref(st))
+    t_arr = np.concatenate([[0.0], (np.arange(T) + 1) * cfg.dt])
+    return t_arr, g, its.value, tr.value, st.value
+
+
+def compute_Q4(cfg: Cfg4, theta, g_new, g_old, alpha=None):
+    A, b = np.zeros(16), np.zeros(4)
+    theta = _f64(theta)
+    lib().orc4_theta_to_matrices(_dptr(theta), _dptr(A), _dptr(b))
+    g_new, g_old = _f64(g_new).copy(), _f64(g_old)
+    phi, psi = g_new[0:4].copy(), g_new[5:9].copy()
+    Q = np.zeros(10)
+    lib().orc4_compute_Q(_dptr(phi), C.c_double(g_new[4]), _dptr(psi), C.c_double(g_new[9]), _dptr(g_old[0:4].copy()),
+                         C.c_double(g_old[4]), _dptr(g_old[5:9].copy()), C.byref(cfg),
+                         C.c_double(cfg.alpha_const if alpha is None else alpha), _dptr(A), _dptr(b), _dptr(Q))
+    return Q
+
+
+def compute_J4(cfg: Cfg4, theta, g_new, g_old, alpha=None):
+    A, b = np.zeros(16), np.zeros(4)
+    theta = _f64(theta)
+    lib().orc4_theta_to_matrices(_dptr(theta), _dptr(A), _dptr(b))
+    g_new, g_old = _f64(g_new).copy(), _f64(g_old)
+    phi, psi = g_new[0:4].copy(), g_new[5:9].copy()
+    K = np.zeros((10, 10))
+    lib().orc4_compute_J(_dptr(phi), C.c_double(g_new[4]), _dptr(psi), _dptr(g_old[0:4].copy()), _dptr(g_old[5:9].copy()),
+                         C.byref(cfg), C.c_double(cfg.alpha_const if alpha is None else alpha), _dptr(A), _dptr(b), _dptr(K))
+    return K
 
 
 def from_hmx_config(hcfg):

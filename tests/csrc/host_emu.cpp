@@ -106,6 +106,25 @@ static void rebase_once(const SolverConsts& K, const double* theta, const double
 
 extern "C" {
 
+// the generic NS-species solver (hmx_legacy.cuh) on the CPU: g_arr [(n_steps + 1), 2 NS + 2]
+int emu_legacy_solve(const hmx_legacy_config* cfg, const double* theta, double* g_arr, uint32_t* status, uint32_t* iters) {
+    LegacyConsts K;
+    make_legacy_consts(*cfg, K);
+    uint32_t st = 0, it = 0;
+    if (cfg->n_species == 4) {
+        legacy_solve<4>(K, theta, st, it, [&](int level, const double (&g)[10]) { memcpy(g_arr + (size_t)level * 10, g, sizeof(g)); });
+    } else if (cfg->n_species == 5) {
+        legacy_solve<5>(K, theta, st, it, [&](int level, const double (&g)[12]) { memcpy(g_arr + (size_t)level * 12, g, sizeof(g)); });
+    } else {
+        return -1;
+    }
+    *status = st;
+    *iters = it;
+    return 0;
+}
+int emu_sizeof_legacy_config(void) { return (int)sizeof(hmx_legacy_config); }
+
+
 // full solve of one (theta, condition): trajectory (optional), logL, counters
 int emu_evaluate(const hmx_config* cfg, int cond, const double* theta, double* g_arr, double* logL,
                  uint32_t* status, uint32_t* iters, uint32_t* trips) {

@@ -7,9 +7,22 @@ import sys
 from helpers import ROOT
 
 
-def test_reference_arm_prints_contract_line():
+import os
+
+import pytest
+
+
+@pytest.mark.parametrize("kind", ["reference", "port"])
+def test_reference_arm_prints_contract_line(kind):
+    """kind = "reference": the reference as shipped from oracle/_ref (build-time snapshot, oracle/make_ref.py); "port": the
+    oracle's C restatement, the fallback when the snapshot is absent."""
+    sys.path.insert(0, str(ROOT))
+    from oracle import make_ref
+
+    if kind == "reference" and not make_ref.build():
+        pytest.skip("no reference tree and no oracle/_ref snapshot on this machine")
     out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
-                         capture_output=True, text=True, timeout=300)
+                         capture_output=True, text=True, timeout=600, env=dict(os.environ, HMX_BENCH_REF_KIND=kind))
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip().startswith("{")]
     assert len(lines) == 1
@@ -18,7 +31,7 @@ def test_reference_arm_prints_contract_line():
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "evals/s" and d["value"] > 0 and d["dtype"] == "f64"
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["kind"] == kind and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"] and "model" not in d["config"]
 

@@ -71,6 +71,39 @@ class HmxCounters(C.Structure):
     ]
 
 
+class HmxLegacyConfig(C.Structure):
+    _fields_ = [
+        ("n_species", C.c_int32), ("dt", C.c_double), ("n_steps", C.c_int32), ("eps", C.c_double), ("Kp1", C.c_double),
+        ("c_const", C.c_double), ("alpha_const", C.c_double), ("max_newton_iter", C.c_int32), ("eta", C.c_double * 5),
+        ("eta_phi", C.c_double * 5), ("phi_init", C.c_double * 5), ("active_species_mask", C.c_int32),
+        ("alpha_switch_level", C.c_int32), ("alpha_before", C.c_double), ("alpha_after", C.c_double),
+    ]
+
+
+def make_legacy_config(n_species=4, dt=1e-5, maxtimestep=500, eps=1e-6, Kp1=1e-4, eta_vec=None, eta_phi_vec=None, c_const=100.0,
+                       alpha_const=100.0, phi_init=0.2, active_species=None, max_newton_iter=50, alpha_switch_level=-1,
+                       alpha_before=None, alpha_after=None) -> HmxLegacyConfig:
+    """Keyword names and defaults of BiofilmNewtonSolver.__init__ (S4:737-781); the alpha schedule resolved to a level."""
+    if n_species not in (4, 5):
+        raise ValueError("n_species must be 4 or 5")
+    c = HmxLegacyConfig()
+    c.n_species = n_species
+    c.dt, c.n_steps, c.eps, c.Kp1 = float(dt), int(maxtimestep), float(eps), float(Kp1)
+    c.c_const, c.alpha_const, c.max_newton_iter = float(c_const), float(alpha_const), int(max_newton_iter)
+    eta = np.ones(n_species) if eta_vec is None else np.asarray(eta_vec, dtype=float)
+    etaphi = np.ones(n_species) if eta_phi_vec is None else np.asarray(eta_phi_vec, dtype=float)
+    pi = np.asarray(phi_init, dtype=float)
+    pi = np.full(n_species, float(pi.flat[0])) if pi.ndim == 0 or pi.size == 1 else np.resize(pi, n_species)
+    for i in range(n_species):
+        c.eta[i], c.eta_phi[i], c.phi_init[i] = eta[i], etaphi[i], pi[i]
+    act = list(range(n_species)) if active_species is None else list(active_species)
+    c.active_species_mask = sum(1 << i for i in set(act) if 0 <= i < n_species)
+    c.alpha_switch_level = int(alpha_switch_level)
+    c.alpha_before = float(alpha_const if alpha_before is None else alpha_before)
+    c.alpha_after = float(alpha_const if alpha_after is None else alpha_after)
+    return c
+
+
 MUT_MAX_DIM = 32
 MUT_MAX_GROUPS = 64
 
@@ -148,7 +181,8 @@ EXPORTS = [
     "hmx_set_timing",
     "hmx_measure_fp64_peak",
     "hmx_mutate", "hmx_mutate_groups", "hmx_trajectory_rows", "hmx_set_latency_kernel", "hmx_cumsum",
-    "hmx_tsm_obs_rows",
+    "hmx_tsm_obs_rows", "hmx_legacy_trajectory_rows",
+    "hmx_population_create", "hmx_population_destroy", "hmx_population_upload", "hmx_population_download",
 ]
 
 
@@ -280,6 +314,11 @@ def load() -> C.CDLL:
     # array arguments are raw addresses (host or device), hence c_void_p everywhere
     lib.hmx_loglik_batch.argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp, vp]
     lib.hmx_trajectory_batch.argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp]
+    lib.hmx_population_create.argtypes = [vp, C.c_int64, C.c_int32, C.POINTER(vp)]
+    lib.hmx_population_destroy.argtypes = [vp, vp]
+    lib.hmx_population_upload.argtypes = [vp, vp, vp, C.c_int64]
+    lib.hmx_population_download.argtypes = [vp, vp, vp, C.c_int64]
+    lib.hmx_legacy_trajectory_rows.argtypes = [vp, C.POINTER(HmxLegacyConfig), vp, C.c_int64, vp, C.c_int32, vp, vp, vp]
     lib.hmx_tsm_obs_rows.argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp]
     lib.hmx_trajectory_rows.argtypes = [vp, vp, vp, C.c_int64, vp, C.c_int32, vp, vp, vp]
     lib.hmx_beta_step.argtypes = [vp, vp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp]

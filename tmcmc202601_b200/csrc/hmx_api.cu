@@ -23,6 +23,7 @@
 #include "hmx_stage.cuh"
 #include "hmx_mutation.cuh"
 #include "hmx_coop.cuh"
+#include "hmx_legacy.cuh"
 
 using namespace hmx;
 
@@ -81,6 +82,7 @@ struct hmx_ctx {
     const int32_t* cur_row_map = nullptr;
     int cur_n_rows = 0;
     DevBuf row_map;
+    std::vector<void*> populations;  // hmx_population_create
 };
 
 namespace {
@@ -491,6 +493,7 @@ void hmx_destroy(hmx_ctx* ctx) {
                       &ctx->m_ll, &ctx->m_status, &ctx->m_in_theta, &ctx->m_in_logL, &ctx->m_out_theta, &ctx->m_out_logL, &ctx->row_map, &ctx->m_groups, &ctx->logL_scratch};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
+    for (void* p : ctx->populations) cudaFree(p);
     if (ctx->d_cond) cudaFree(ctx->d_cond);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_sched) cudaFree(ctx->d_sched);
@@ -502,6 +505,53 @@ void hmx_destroy(hmx_ctx* ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
+}
+
+// ---- device-resident arrays owned by the context ---------------------------------------------------------
+int hmx_population_create(hmx_ctx* ctx, int64_t n_rows, int32_t n_cols, double** dev) {
+    if (!ctx) return HMX_ERR_INVALID;
+    if (!dev || n_rows < 0 || n_cols < 1) return fail(ctx, HMX_ERR_INVALID, "hmx_population_create: bad arguments");
+    *dev = nullptr;
+    CU(cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    const size_t bytes = std::max<size_t>((size_t)n_rows * (size_t)n_cols * sizeof(double), 256);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, HMX_ERR_OOM, std::string("hmx_population_create: cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    }
+    ctx->populations.push_back(p);
+    *dev = (double*)p;
+    return HMX_OK;
+}
+
+int hmx_population_destroy(hmx_ctx* ctx, double* dev) {
+    if (!ctx) return HMX_ERR_INVALID;
+    auto it = std::find(ctx->populations.begin(), ctx->populations.end(), (void*)dev);
+    if (it == ctx->populations.end()) return fail(ctx, HMX_ERR_INVALID, "hmx_population_destroy: not an array of this context");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(*it);
+    ctx->populations.erase(it);
+    return HMX_OK;
+}
+
+int hmx_population_upload(hmx_ctx* ctx, double* dev, const double* host, int64_t n_values) {
+    if (!ctx) return HMX_ERR_INVALID;
+    if (n_values < 0 || (n_values > 0 && (!dev || !host))) return fail(ctx, HMX_ERR_INVALID, "hmx_population_upload: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    // asynchronous for pinned sources; a pageable source is staged by the runtime before the call returns
+    if (n_values) CU(cudaMemcpyAsync(dev, host, (size_t)n_values * sizeof(double), cudaMemcpyDefault, ctx->stream));
+    return HMX_OK;
+}
+
+int hmx_population_download(hmx_ctx* ctx, double* host, const double* dev, int64_t n_values) {
+    if (!ctx) return HMX_ERR_INVALID;
+    if (n_values < 0 || (n_values > 0 && (!dev || !host))) return fail(ctx, HMX_ERR_INVALID, "hmx_population_download: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    if (n_values) CU(cudaMemcpyAsync(host, dev, (size_t)n_values * sizeof(double), cudaMemcpyDefault, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return HMX_OK;
 }
 
 int hmx_set_stream(hmx_ctx* ctx, void* cuda_stream) {
@@ -569,6 +619,70 @@ int hmx_trajectory_rows(hmx_ctx* ctx, const double* theta, const int32_t* cond_i
     ctx->cur_row_map = nullptr;
     ctx->cur_n_rows = 0;
     return rc;
+}
+
+int hmx_legacy_trajectory_rows(hmx_ctx* ctx, const hmx_legacy_config* cfg, const double* theta, int64_t N, const int32_t* rows,
+                               int32_t n_rows, double* g, uint32_t* status, uint32_t* newton_iters) {
+    if (!ctx) return HMX_ERR_INVALID;
+    if (!cfg || N < 0 || (N > 0 && (!theta || !g))) return fail(ctx, HMX_ERR_INVALID, "hmx_legacy_trajectory_rows: NULL argument or N < 0");
+    if (cfg->n_species != 4 && cfg->n_species != 5) return fail(ctx, HMX_ERR_INVALID, "hmx_legacy_trajectory_rows: n_species must be 4 or 5");
+    if (!(cfg->dt > 0.0) || cfg->n_steps < 1 || cfg->max_newton_iter < 1)
+        return fail(ctx, HMX_ERR_INVALID, "hmx_legacy_trajectory_rows: dt > 0, n_steps >= 1, max_newton_iter >= 1 required");
+    const int NS = cfg->n_species, NG = 2 * NS + 2, NTH = NS == 4 ? 14 : 20, T = cfg->n_steps;
+    for (int i = 0; i < NS; ++i)
+        if (!(cfg->eta[i] != 0.0)) return fail(ctx, HMX_ERR_INVALID, "hmx_legacy_trajectory_rows: eta must be non-zero");
+    if (rows && (n_rows < 1 || n_rows > T + 1)) return fail(ctx, HMX_ERR_INVALID, "hmx_legacy_trajectory_rows: need 1 <= n_rows <= n_steps + 1");
+    if (rows && is_device_ptr(rows)) return fail(ctx, HMX_ERR_INVALID, "hmx_legacy_trajectory_rows: rows must be a host array");
+    CU(cudaSetDevice(ctx->device));
+    if (N == 0) return HMX_OK;
+    LegacyParams P;
+    make_legacy_consts(*cfg, P.K);
+    const int out_rows = rows ? n_rows : T + 1;
+    int rc;
+    P.row_map = nullptr;
+    if (rows) {
+        std::vector<int32_t> m((size_t)T + 1, -1);
+        for (int r = 0; r < n_rows; ++r) {
+            if (rows[r] < 0 || rows[r] > T || (r > 0 && rows[r] <= rows[r - 1]))
+                return fail(ctx, HMX_ERR_INVALID, "hmx_legacy_trajectory_rows: rows must be strictly ascending in [0, n_steps]");
+            m[rows[r]] = r;
+        }
+        if ((rc = ensure(ctx, ctx->row_map, m.size() * sizeof(int32_t)))) return rc;
+        CU(cudaMemcpyAsync(ctx->row_map.p, m.data(), m.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));  // `m` dies with this scope
+        P.row_map = (const int32_t*)ctx->row_map.p;
+    }
+    const long long stride = (long long)out_rows * NG;
+    const long long chunk = std::max(1ll, std::min(ctx->chunk_evals, (8ll << 30) / (stride * 8)));
+    bool need_sync = false;
+    for (long long off = 0; off < N; off += chunk) {
+        const long long n = std::min(chunk, N - off);
+        const void* d_theta;
+        void *d_g, *h_g, *d_st, *h_st, *d_it, *h_it;
+        if ((rc = stage_in(ctx, theta + off * NTH, (size_t)n * NTH * sizeof(double), ctx->theta, &d_theta))) return rc;
+        if ((rc = stage_out(ctx, g + off * stride, (size_t)n * stride * sizeof(double), ctx->traj, &d_g, &h_g))) return rc;
+        if ((rc = stage_out(ctx, status ? status + off : nullptr, (size_t)n * sizeof(uint32_t), ctx->st_out0, &d_st, &h_st))) return rc;
+        if ((rc = stage_out(ctx, newton_iters ? newton_iters + off : nullptr, (size_t)n * sizeof(uint32_t), ctx->st_out1, &d_it, &h_it))) return rc;
+        P.theta = (const double*)d_theta;
+        P.N = n;
+        P.traj = (double*)d_g;
+        P.n_rows = out_rows;
+        P.status = (uint32_t*)d_st;
+        P.iters = (uint32_t*)d_it;
+        const int blocks = (int)((n + 127) / 128);
+        if (NS == 4) legacy_ode_kernel<4><<<blocks, 128, 0, ctx->stream>>>(P);
+        else legacy_ode_kernel<5><<<blocks, 128, 0, ctx->stream>>>(P);
+        CU(cudaGetLastError());
+        ++ctx->launches;
+        if (h_g) CU(cudaMemcpyAsync(h_g, d_g, (size_t)n * stride * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (h_st) CU(cudaMemcpyAsync(h_st, d_st, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (h_it) CU(cudaMemcpyAsync(h_it, d_it, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        const bool any_host = h_g || h_st || h_it;
+        need_sync = need_sync || any_host;
+        if (off + chunk < N && (any_host || !is_device_ptr(theta))) CU(cudaStreamSynchronize(ctx->stream));
+    }
+    if (need_sync) CU(cudaStreamSynchronize(ctx->stream));
+    return HMX_OK;
 }
 
 int hmx_beta_step(hmx_ctx* ctx, const double* logL, int64_t N, double beta, double target_ess_ratio,

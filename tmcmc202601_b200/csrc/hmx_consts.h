@@ -100,3 +100,41 @@ inline void make_cond_consts(const hmx_config& c, int k, CondConsts& q) {
 }
 
 }  // namespace hmx
+
+#include "hmx_legacy.cuh"
+
+namespace hmx {
+
+// hmx_legacy_config -> kernel constants of the generic NS-species solver (initial state: S4:857-865)
+inline void make_legacy_consts(const hmx_legacy_config& c, LegacyConsts& K) {
+    memset(&K, 0, sizeof(K));
+    const int NS = c.n_species;
+    K.dt = c.dt;
+    K.inv_dt = 1.0 / c.dt;
+    K.eps = c.eps;
+    K.Kp1 = c.Kp1;
+    K.c = c.c_const;
+    K.alpha_const = c.alpha_const;
+    K.alpha_before = c.alpha_before;
+    K.alpha_after = c.alpha_after;
+    K.switch_level = c.alpha_switch_level;
+    K.n_steps = c.n_steps;
+    K.max_iter = c.max_newton_iter;
+    K.active_mask = (uint32_t)c.active_species_mask & ((1u << NS) - 1u);
+    double sum = 0.0;
+    for (int i = 0; i < NS; ++i) {
+        K.eta[i] = c.eta[i];
+        K.eta_phi[i] = c.eta_phi[i];
+        K.inv_eta[i] = 1.0 / c.eta[i];
+        K.c_eta[i] = c.c_const / c.eta[i];
+        K.etaphi_eta[i] = c.eta_phi[i] / c.eta[i];
+        const bool act = (K.active_mask >> i) & 1u;
+        K.g0[i] = act ? c.phi_init[i] : 0.0;
+        sum += K.g0[i];
+        K.g0[NS + 1 + i] = act ? 0.999 : 0.0;
+    }
+    K.g0[NS] = 1.0 - sum;
+    K.g0[2 * NS + 1] = 0.0;
+}
+
+}  // namespace hmx

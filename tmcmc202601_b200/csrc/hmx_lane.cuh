@@ -143,7 +143,7 @@ HMX_HD bool lane_advance(const SolverConsts& K, Lane& s) {
 // convergence into a trip that also computes the next step's first direction.
 // x: the raw accepted trial (== s.g == new s.gp); gp5_old: phi_0 of the previous level before the advance.
 HMX_HD bool rebase_residual(const SolverConsts& K, const Lane& s, const double (&x)[12], double gp5_old, Eval& e) {
-    double nr[6], as[6];
+    unsigned long long nb[6];
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
         const double v = e.ph[i], u = e.ps[i];
@@ -155,19 +155,17 @@ HMX_HD bool rebase_residual(const SolverConsts& K, const Lane& s, const double (
         const double qs = e.Q[6 + i] + fma(e.p[i], dph, v * v * dps);
         e.Q[i] = qi;
         e.Q[6 + i] = qs;
-        nr[i] = max_abs(qi, qs);
-        as[i] = fabs(qi) + fabs(qs);
+        nb[i] = umax64(abs_bits(qi), abs_bits(qs));
     }
     const double ph0 = clip01(x[5]);
     e.Q[5] = e.Q[5] + ((ph0 - s.gp[5]) - (ph0 - gp5_old)) * K.inv_dt;
-    nr[5] = max_abs(e.Q[5], e.Q[11]);
-    as[5] = fabs(e.Q[5]) + fabs(e.Q[11]);
-    e.norm = max_abs(max_abs(max_abs(nr[0], nr[1]), max_abs(nr[2], nr[3])), max_abs(nr[4], nr[5]));
-    const double asum = ((as[0] + as[1]) + (as[2] + as[3])) + (as[4] + as[5]);
-    e.nan = (asum != asum);
-    // A non-finite component of x makes (clip(x) - x)/dt, hence the sum, non-finite (gamma entered the accepted
-    // residual itself, which was finite): this test doubles as the trajectory's isfinite scan (EV:657-667).
-    return asum <= 1.7976931348623157e308;
+    nb[5] = umax64(abs_bits(e.Q[5]), abs_bits(e.Q[11]));
+    const unsigned long long m = umax64(umax64(umax64(nb[0], nb[1]), umax64(nb[2], nb[3])), umax64(nb[4], nb[5]));
+    e.norm = bits_double(m);
+    e.nan = m > kInfBits;
+    // A non-finite component of x makes (clip(x) - x)/dt, hence a residual component, non-finite (gamma entered the
+    // accepted residual itself, which was finite): this test doubles as the trajectory's isfinite scan (EV:657-667).
+    return m < kInfBits;
 }
 
 // One trip.  `step_end(g, gp, step_idx)` is called whenever the Newton loop of the current time step has ended,

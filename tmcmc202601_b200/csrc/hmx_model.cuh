@@ -32,6 +32,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define HMX_HD __host__ __device__ __forceinline__
@@ -78,12 +79,53 @@ HMX_HD double clip01(double v) {
     return (v < kClipLo) ? kClipLo : ((v > kClipHi) ? kClipHi : v);
 }
 
+// Strictly-inside-the-box test on the HIGH 32-bit word only (one integer subtract + one unsigned compare on the ALU
+// instead of two DSETP on the FP64 pipe): bits(1e-12) = 0x3D719799_812DEA11 and bits(1 - 1e-12) = 0x3FEFFFFF_FFFFDCD0, so
+// 0x3D71979A <= hi32(v) < 0x3FEFFFFF implies 1e-12 < v < 1 - 1e-12.  Negative values, NaN, inf and the two thin bands next to
+// the bounds fail the test and take the exact clip (clip01) -- the test is conservative, never wrong.
+HMX_HD bool strictly_inside_hi(double v) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t h = (uint32_t)__double2hiint(v);
+#else
+    unsigned long long u;
+    memcpy(&u, &v, sizeof(u));
+    const uint32_t h = (uint32_t)(u >> 32);
+#endif
+    return (h - 0x3D71979Au) < (0x3FEFFFFFu - 0x3D71979Au);
+}
+
 // max(|a|, |b|) as one ordered compare and a select.  fmax() costs twice the instructions because of its NaN
 // rules; the callers detect NaN separately (sum of |Q|) and never use the maximum when one is present.
 HMX_HD double max_abs(double a, double b) {
     const double fa = fabs(a), fb = fabs(b);
     return (fa > fb) ? fa : fb;
 }
+
+// |a| as its IEEE-754 bit pattern.  For non-negative doubles the order of the patterns (as unsigned integers) IS the
+// order of the values, +inf is 0x7ff0..0 and every NaN pattern lies above it.  The infinity norm of the residual, its
+// NaN test (S5:342-348) and the finiteness scan are therefore ONE unsigned-integer max tree on the ALU instead of
+// DSETP / DADD work on the FP64 pipe, which is the pipe this kernel is bound by (ncu r02a: the compare-select maximum and
+// the |Q| sum were 63 of ~1030 FP64-pipe instructions per trip).  The resulting double is bit-identical.
+constexpr unsigned long long kInfBits = 0x7ff0000000000000ull;
+HMX_HD unsigned long long abs_bits(double a) {
+#if defined(__CUDA_ARCH__)
+    return (unsigned long long)__double_as_longlong(a) & 0x7fffffffffffffffull;
+#else
+    unsigned long long u;
+    memcpy(&u, &a, sizeof(u));
+    return u & 0x7fffffffffffffffull;
+#endif
+}
+HMX_HD double bits_double(unsigned long long u) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)u);
+#else
+    double a;
+    memcpy(&a, &u, sizeof(a));
+    return a;
+#endif
+}
+HMX_HD unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
 
 // packed symmetric A: index of (i,j)
 HMX_HD constexpr int apk(int i, int j) {
@@ -166,11 +208,15 @@ HMX_HD void residual(const SolverConsts& K, const double (&x)[12], const GPT& gp
     const double gam = x[11];
     // phi, psi inside the box is the overwhelmingly common case: one ordered compare pair per value and a
     // branch around the selects (NaN fails the test and takes the clip path, which leaves it NaN like S5:66-69)
-#if defined(HMX_CLIP_BRANCH)
+#if defined(HMX_CLIP_BRANCH) || defined(HMX_CLIP_HIWORD)
     bool inbox = true;
 #pragma unroll
     for (int i = 0; i < 5; ++i)
+#if defined(HMX_CLIP_HIWORD)
+        inbox = inbox && strictly_inside_hi(x[i]) && strictly_inside_hi(x[6 + i]);
+#else
         inbox = inbox && (x[i] >= kClipLo) && (x[i] <= kClipHi) && (x[6 + i] >= kClipLo) && (x[6 + i] <= kClipHi);
+#endif
     if (inbox) {
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
@@ -235,7 +281,7 @@ HMX_HD void residual(const SolverConsts& K, const double (&x)[12], const GPT& gp
         }
         e.I[4] *= e.h;
     }
-    double nr[6], as[6];  // per-row partial max / sum of |Q|: reduced as trees to keep the dependency chain short
+    unsigned long long nb[6];  // per-species max of |Q| as bit patterns: reduced as a tree to keep the dependency chain short
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
         const double v = e.ph[i], u = e.ps[i];
@@ -247,16 +293,14 @@ HMX_HD void residual(const SolverConsts& K, const double (&x)[12], const GPT& gp
         if (ALPHA) qs += (b[i] * K.alpha_eta[i]) * u;
         e.Q[i] = qi;
         e.Q[6 + i] = qs;
-        nr[i] = max_abs(qi, qs);
-        as[i] = fabs(qi) + fabs(qs);
+        nb[i] = umax64(abs_bits(qi), abs_bits(qs));
     }
     e.Q[5] = gam + f0 + (ph0 - gp[5]) * K.inv_dt;                                  // S5:109-113
     e.Q[11] = ((((e.ph[0] + e.ph[1]) + e.ph[2]) + e.ph[3]) + e.ph[4]) + ph0 - 1.0;    // S5:126
-    nr[5] = max_abs(e.Q[5], e.Q[11]);
-    as[5] = fabs(e.Q[5]) + fabs(e.Q[11]);
-    e.norm = max_abs(max_abs(max_abs(nr[0], nr[1]), max_abs(nr[2], nr[3])), max_abs(nr[4], nr[5]));
-    const double asum = ((as[0] + as[1]) + (as[2] + as[3])) + (as[4] + as[5]);
-    e.nan = (asum != asum);  // true for NaN only (a sum of |.| is +inf, not NaN, for infinite entries): S5:342-348
+    nb[5] = umax64(abs_bits(e.Q[5]), abs_bits(e.Q[11]));
+    const unsigned long long m = umax64(umax64(umax64(nb[0], nb[1]), umax64(nb[2], nb[3])), umax64(nb[4], nb[5]));
+    e.norm = bits_double(m);  // ||Q||_inf (a NaN pattern when a NaN is present: every comparison with it is false)
+    e.nan = m > kInfBits;     // any(isnan(Q)): true for NaN only, +inf entries are not NaN (S5:342-348)
 }
 
 // 5x5 solve with two right-hand sides.  S[r][0..4] matrix, S[r][5], S[r][6] the two right-hand sides ->

@@ -20,7 +20,8 @@ class HmxError(RuntimeError):
 
 
 def _is_torch(x) -> bool:
-    return type(x).__module__.startswith("torch")
+    """Device-resident argument: a CUDA torch tensor or a DeviceArray of this module (anything with data_ptr())."""
+    return hasattr(x, "data_ptr")
 
 
 def _addr(x) -> Optional[int]:
@@ -29,6 +30,56 @@ def _addr(x) -> Optional[int]:
     if _is_torch(x):
         return x.data_ptr()
     return x.ctypes.data
+
+
+def _arg(x, dtype=np.float64):
+    """NumPy input -> contiguous array of `dtype`; device-resident input passes through."""
+    if x is None or _is_torch(x):
+        return x
+    return np.ascontiguousarray(x, dtype=dtype)
+
+
+class DeviceArray:
+    """Row-major float64 array living on the engine's GPU (hmx_population_create): upload once, pass to any engine
+    call in place of a NumPy array.  Row slices (`a[lo:hi]`) are views; the owner frees the memory."""
+
+    def __init__(self, engine: "HamiltonEngine", ptr: int, shape, owner: bool = True):
+        self._engine, self._ptr, self.shape, self._owner = engine, int(ptr), tuple(int(v) for v in shape), owner
+
+    def data_ptr(self) -> int:
+        return self._ptr
+
+    @property
+    def size(self) -> int:
+        return int(np.prod(self.shape)) if self.shape else 1
+
+    def __getitem__(self, sl):
+        if not isinstance(sl, slice) or sl.step not in (None, 1):
+            raise TypeError("DeviceArray supports contiguous row slices only")
+        lo, hi, _ = sl.indices(self.shape[0])
+        row = int(np.prod(self.shape[1:])) if len(self.shape) > 1 else 1
+        return DeviceArray(self._engine, self._ptr + lo * row * 8, (max(hi - lo, 0),) + self.shape[1:], owner=False)
+
+    def upload(self, host):
+        host = np.ascontiguousarray(host, dtype=np.float64)
+        if host.size != self.size:
+            raise ValueError(f"upload of {host.size} values into a DeviceArray of {self.size}")
+        e = self._engine
+        e._check(e._lib.hmx_population_upload(e._ctx, self._ptr, host.ctypes.data, host.size), "hmx_population_upload")
+        self._keepalive = host  # the copy is asynchronous: keep the source alive until the next synchronising call
+        return self
+
+    def numpy(self) -> np.ndarray:
+        out = np.empty(self.shape, dtype=np.float64)
+        e = self._engine
+        e._check(e._lib.hmx_population_download(e._ctx, out.ctypes.data, self._ptr, out.size), "hmx_population_download")
+        return out
+
+    def free(self):
+        if self._owner and self._ptr and self._engine._ctx:
+            e = self._engine
+            e._check(e._lib.hmx_population_destroy(e._ctx, self._ptr), "hmx_population_destroy")
+        self._ptr = 0
 
 
 class HamiltonEngine:
@@ -67,20 +118,33 @@ class HamiltonEngine:
         """Enqueue on torch's current CUDA stream (needed before passing CUDA tensors)."""
         import torch
 
-        self._check(self._lib.hmx_set_stream(self._ctx, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "hmx_set_stream")
+        h = int(torch.cuda.current_stream(self.device).cuda_stream)
+        # torch's default stream is the legacy default stream, whose handle is 0 == NULL == "use the context's own stream" in
+        # hmx_set_stream; cudaStreamLegacy (handle 1) names it explicitly, so the library's work is ordered with torch's
+        self._check(self._lib.hmx_set_stream(self._ctx, C.c_void_p(h if h != 0 else 1)), "hmx_set_stream")
 
     def synchronize(self):
         self._check(self._lib.hmx_synchronize(self._ctx), "hmx_synchronize")
 
+    def device_array(self, shape, host=None) -> DeviceArray:
+        """A context-owned device array (hmx_population_create), optionally filled from `host`."""
+        shape = tuple(int(v) for v in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        rows = shape[0]
+        cols = int(np.prod(shape[1:])) if len(shape) > 1 else 1
+        p = C.c_void_p()
+        self._check(self._lib.hmx_population_create(self._ctx, rows, max(cols, 1), C.byref(p)), "hmx_population_create")
+        a = DeviceArray(self, p.value or 0, shape)
+        return a.upload(host) if host is not None else a
+
     # -- hot path ---------------------------------------------------------------------------------------
     def loglik_batch(self, theta, cond_id=None, return_status=False, return_obs=False):
         """logL[N] for FULL 20-vectors theta[N,20] (hmx_loglik_batch).  NumPy in -> NumPy out."""
-        theta = np.ascontiguousarray(theta, dtype=np.float64)
-        if theta.ndim != 2 or theta.shape[1] != _abi.NTHETA:
+        theta = _arg(theta)  # a DeviceArray / CUDA tensor (uploaded once per stage) is used in place
+        if len(theta.shape) != 2 or theta.shape[1] != _abi.NTHETA:
             raise ValueError("theta must have shape (N, 20)")
         N = theta.shape[0]
-        cid = None if cond_id is None else np.ascontiguousarray(cond_id, dtype=np.int32)
-        if cid is not None and (cid.shape != (N,) or (N and (cid.min() < 0 or cid.max() >= self.n_cond))):
+        cid = _arg(cond_id, np.int32)
+        if cid is not None and not _is_torch(cid) and (cid.shape != (N,) or (N and (cid.min() < 0 or cid.max() >= self.n_cond))):
             raise ValueError("cond_id must have shape (N,) with values in [0, n_cond)")
         logL = np.empty(N, dtype=np.float64)
         status = np.zeros(N, dtype=np.uint32) if return_status else None
@@ -166,6 +230,22 @@ class HamiltonEngine:
             off += n
         return out
 
+    def legacy_trajectory_rows(self, legacy_cfg: "_abi.HmxLegacyConfig", theta, rows=None):
+        """The legacy 4-species solver (hmx_legacy_trajectory_rows): g[N, len(rows) | T+1, 10], status[N], iters[N]."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        nth = 14 if legacy_cfg.n_species == 4 else 20
+        if theta.ndim != 2 or theta.shape[1] != nth:
+            raise ValueError(f"theta must have shape (N, {nth})")
+        N = theta.shape[0]
+        r = None if rows is None else np.ascontiguousarray(rows, dtype=np.int32).reshape(-1)
+        n_rows = legacy_cfg.n_steps + 1 if r is None else r.size
+        g = np.empty((N, n_rows, 2 * legacy_cfg.n_species + 2))
+        status = np.zeros(N, dtype=np.uint32)
+        iters = np.zeros(N, dtype=np.uint32)
+        self._check(self._lib.hmx_legacy_trajectory_rows(self._ctx, C.byref(legacy_cfg), _addr(theta), N, _addr(r), 0 if r is None else r.size,
+                                                         _addr(g), _addr(status), _addr(iters)), "hmx_legacy_trajectory_rows")
+        return g, status, iters
+
     def trajectory_rows(self, theta, rows, cond_id=None):
         """g[N, len(rows), 12]: the time levels `rows` (strictly ascending) of every trajectory (hmx_trajectory_rows)."""
         theta = np.ascontiguousarray(theta, dtype=np.float64)
@@ -205,7 +285,7 @@ class HamiltonEngine:
 
     # -- stage arithmetic -------------------------------------------------------------------------------
     def beta_step(self, logL, beta, target_ess_ratio=0.5, min_delta_beta=0.02, max_delta_beta=0.5):
-        logL = logL if _is_torch(logL) else np.ascontiguousarray(logL, dtype=np.float64)
+        logL = _arg(logL)
         db, ess = C.c_double(0.0), C.c_double(0.0)
         self._check(
             self._lib.hmx_beta_step(self._ctx, _addr(logL), logL.shape[0], beta, target_ess_ratio, min_delta_beta, max_delta_beta,
@@ -215,8 +295,8 @@ class HamiltonEngine:
         return db.value, ess.value
 
     def weights(self, logL, delta_beta):
-        logL = np.ascontiguousarray(logL, dtype=np.float64)
-        w = np.empty_like(logL)
+        logL = _arg(logL)
+        w = np.empty(logL.shape[0], dtype=np.float64)
         ls = C.c_double(0.0)
         self._check(self._lib.hmx_weights(self._ctx, _addr(logL), logL.shape[0], delta_beta, _addr(w), C.addressof(ls)), "hmx_weights")
         return w, ls.value
@@ -229,31 +309,27 @@ class HamiltonEngine:
         return cs
 
     def resample(self, w, u):
-        w = np.ascontiguousarray(w, dtype=np.float64)
+        w = _arg(w)
         idx = np.empty(w.shape[0], dtype=np.int64)
         self._check(self._lib.hmx_resample(self._ctx, _addr(w), w.shape[0], float(u), _addr(idx)), "hmx_resample")
         return idx
 
     def weighted_cov(self, theta, w):
-        theta = np.ascontiguousarray(theta, dtype=np.float64)
-        w = np.ascontiguousarray(w, dtype=np.float64)
+        theta, w = _arg(theta), _arg(w)
         N, d = theta.shape
         mean, cov = np.empty(d), np.empty((d, d))
         self._check(self._lib.hmx_weighted_cov(self._ctx, _addr(theta), _addr(w), N, d, _addr(mean), _addr(cov)), "hmx_weighted_cov")
         return mean, cov
 
     def weighted_moments(self, theta, w):
-        theta = np.ascontiguousarray(theta, dtype=np.float64)
-        w = np.ascontiguousarray(w, dtype=np.float64)
+        theta, w = _arg(theta), _arg(w)
         N, d = theta.shape
         m = np.empty(2 + d)
         self._check(self._lib.hmx_weighted_moments(self._ctx, _addr(theta), _addr(w), N, d, _addr(m)), "hmx_weighted_moments")
         return m
 
     def weighted_scatter(self, theta, w, mean):
-        theta = np.ascontiguousarray(theta, dtype=np.float64)
-        w = np.ascontiguousarray(w, dtype=np.float64)
-        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        theta, w, mean = _arg(theta), _arg(w), _arg(mean)
         N, d = theta.shape
         s = np.empty((d, d))
         self._check(self._lib.hmx_weighted_scatter(self._ctx, _addr(theta), _addr(w), N, d, _addr(mean), _addr(s)), "hmx_weighted_scatter")
