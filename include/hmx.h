@@ -143,6 +143,21 @@ int hmx_loglik_batch(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, 
 int hmx_tsm_obs_rows(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, int64_t N, double* x0, double* sigma2,
                      double* x1, double* logL, uint32_t* status);
 
+/* replaces: jax.value_and_grad(log_likelihood) as the reference's NUTS / HMC engine consumes it
+ * (data_5species/main/tmcmc_nuts_engine.py:202; leapfrog :20-34, tempered_vg :247-249): value and gradient of the
+ * log-likelihood of hmx_loglik_batch for a batch of FULL 20-vectors.
+ *   grad   [N,20]  d logL / d theta_k for all 20 parameters, by forward sensitivities of the implicit-Euler trajectory through
+ *                  all n_steps levels (exact Jacobian; csrc/hmx_grad.cuh), with the likelihood variance (sigma_obs^2 + the TSM
+ *                  variance) frozen at theta.  Evaluations flagged HMX_ST_NONFINITE get logL = -1e20 and a zero gradient.
+ *   dstate [N,n_obs_max,12,20] or NULL: the state sensitivities d g[idx_sparse] / d theta behind it, from which the gradient of
+ *                  any other observable-based likelihood (e.g. the normalised-fraction Gaussian of
+ *                  estimate_reduced_nishioka_jax.py:115-133) follows by the chain rule.
+ * The gradient is that of the converged implicit-Euler map evaluated on the solver's trajectory (which carries the Newton
+ * tolerance eps): it equals central differences of a tightly converged solve to <= 1e-6, and differs from them by O(eps)-level
+ * relative amounts (1e-4 observed) at the production tolerance. */
+int hmx_loglik_grad_batch(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, int64_t N, double* logL, double* grad,
+                          double* dstate, uint32_t* status);
+
 /* replaces: BiofilmNewtonSolver5S.run_deterministic / .solve (S5:561-581, 646) for a batch.
  *   g [N,n_steps+1,12] row-major;  t_arr is (arange(n_steps+1) * dt) and is left to the caller. */
 int hmx_trajectory_batch(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, int64_t N,

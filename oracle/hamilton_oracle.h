@@ -127,6 +127,13 @@ void orc_resample(const double* w, int64_t N, double u, int64_t* idx);
 void orc_weighted_cov(const double* theta, const double* w, int64_t N, int d, double* mean,
                       double* cov);
 
+/* ---- likelihood gradient (hamilton_oracle_grad.c): forward sensitivities with the EXACT Jacobian; parity unpinned against
+ * the reference (which has no such code), pinned by finite differences of the pinned oracle ---- */
+void orc_exact_jacobians(const orc_solver_cfg* cfg, const double* theta, const double* g_new, const double* g_old,
+                         double* Jx /*[144]*/, double* Jp_diag /*[22]*/);
+double orc_loglik_grad(const orc_solver_cfg* cfg, const orc_cond_cfg* cond, const double* theta, double* grad /*[20]*/,
+                       double* dstate /*[n_obs,12,20] or NULL*/, uint32_t* status);
+
 /* ---- legacy 4-species solver (S4 = improved1207_paper_jit.py, class BiofilmNewtonSolver): hamilton_oracle4.c ---- */
 typedef struct {
     double dt;

@@ -59,7 +59,7 @@ class CondCfg(C.Structure):
 
 def build(force: bool = False) -> Path:
     """Compile the oracle with the committed Makefile (gcc only; a couple of seconds)."""
-    srcs = [_HERE / "hamilton_oracle.c", _HERE / "hamilton_oracle4.c", _HERE / "hamilton_oracle.h"]
+    srcs = [_HERE / "hamilton_oracle.c", _HERE / "hamilton_oracle4.c", _HERE / "hamilton_oracle_grad.c", _HERE / "hamilton_oracle.h"]
     if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < max(p.stat().st_mtime for p in srcs):
         subprocess.run(["make", "-C", str(_HERE)], check=True, capture_output=True)
     return _LIB_PATH
@@ -79,6 +79,7 @@ def lib() -> C.CDLL:
         _lib.orc_newton_step.restype = C.c_int
         _lib.orc_dgesv.restype = C.c_int
         _lib.orc_weights.restype = C.c_int
+        _lib.orc_loglik_grad.restype = C.c_double
         del dp
     return _lib
 
@@ -287,6 +288,24 @@ def weighted_cov(theta, w):
     mean, cov = np.empty(d), np.empty((d, d))
     lib().orc_weighted_cov(_dptr(theta), _dptr(w), C.c_int64(N), C.c_int(d), _dptr(mean), _dptr(cov))
     return mean, cov
+
+
+# ---- likelihood gradient (hamilton_oracle_grad.c) --------------------------------------------------------------------
+def loglik_grad(cfg: SolverCfg, cond: CondCfg, theta, want_dstate=False):
+    """(logL, grad[20][, dstate[n_obs,12,20]]): forward sensitivities with the exact Jacobian, variance frozen."""
+    theta = _f64(theta)
+    grad = np.zeros(NTHETA)
+    ds = np.zeros((cond.n_obs, NSTATE, NTHETA))
+    st = C.c_uint32(0)
+    ll = lib().orc_loglik_grad(C.byref(cfg), C.byref(cond), _dptr(theta), _dptr(grad), _dptr(ds), C.byref(st))
+    return (ll, grad, ds) if want_dstate else (ll, grad)
+
+
+def exact_jacobians(cfg: SolverCfg, theta, g_new, g_old):
+    theta, g_new, g_old = _f64(theta), _f64(g_new), _f64(g_old)
+    Jx, Jp = np.zeros((12, 12)), np.zeros((11, 2))
+    lib().orc_exact_jacobians(C.byref(cfg), _dptr(theta), _dptr(g_new), _dptr(g_old), _dptr(Jx), _dptr(Jp))
+    return Jx, Jp
 
 
 # ---- legacy 4-species solver (hamilton_oracle4.c) ------------------------------------------------------------------

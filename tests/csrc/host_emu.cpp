@@ -9,6 +9,7 @@
 
 #include "../../tmcmc202601_b200/csrc/hmx_obs.cuh"
 #include "../../tmcmc202601_b200/csrc/hmx_mutation.cuh"
+#include "../../tmcmc202601_b200/csrc/hmx_grad.cuh"
 
 using namespace hmx;
 
@@ -104,6 +105,25 @@ static void rebase_once(const SolverConsts& K, const double* theta, const double
         }                                                   \
     } while (0)
 
+// forward-sensitivity recursion of hmx_grad.cuh over a stored trajectory g_arr [(n_steps + 1), 12]: S_out [n_rows,12] at `rows`
+template <bool ALPHA, int HILL>
+static void emu_sens(const SolverConsts& K, const double* theta, const double* g_arr, int k, const int32_t* rows, int n_rows, double* S_out) {
+    ThetaMap tm = {HMX_THETA_P, HMX_THETA_Q};
+    double A[15], b[5], S[12], x[12], gp[11];
+    theta_to_Ab(theta, A, b);
+    for (int i = 0; i < 12; ++i) S[i] = 0.0;
+    int nr = 0;
+    for (int t = 1; t <= K.n_steps && nr < n_rows; ++t) {
+        for (int i = 0; i < 12; ++i) x[i] = g_arr[(size_t)t * 12 + i];
+        for (int i = 0; i < 11; ++i) gp[i] = g_arr[(size_t)(t - 1) * 12 + i];
+        sensitivity_step<ALPHA, HILL>(K, x, gp, A, b, tm.p[k], tm.q[k], S);
+        while (nr < n_rows && rows[nr] == t) {
+            memcpy(S_out + (size_t)nr * 12, S, sizeof(S));
+            ++nr;
+        }
+    }
+}
+
 extern "C" {
 
 // the generic NS-species solver (hmx_legacy.cuh) on the CPU: g_arr [(n_steps + 1), 2 NS + 2]
@@ -120,6 +140,22 @@ int emu_legacy_solve(const hmx_legacy_config* cfg, const double* theta, double* 
     }
     *status = st;
     *iters = it;
+    return 0;
+}
+int emu_sensitivities(const hmx_config* cfg, const double* theta, const double* g_arr, int k, const int32_t* rows, int n_rows, double* S_out) {
+    SolverConsts K;
+    make_solver_consts(*cfg, K);
+    const bool alpha = cfg->alpha_const != 0.0;
+    const int hill = hill_variant(K);
+    if (alpha) {
+        if (hill == 0) emu_sens<true, 0>(K, theta, g_arr, k, rows, n_rows, S_out);
+        else if (hill == 1) emu_sens<true, 1>(K, theta, g_arr, k, rows, n_rows, S_out);
+        else emu_sens<true, 2>(K, theta, g_arr, k, rows, n_rows, S_out);
+    } else {
+        if (hill == 0) emu_sens<false, 0>(K, theta, g_arr, k, rows, n_rows, S_out);
+        else if (hill == 1) emu_sens<false, 1>(K, theta, g_arr, k, rows, n_rows, S_out);
+        else emu_sens<false, 2>(K, theta, g_arr, k, rows, n_rows, S_out);
+    }
     return 0;
 }
 int emu_sizeof_legacy_config(void) { return (int)sizeof(hmx_legacy_config); }

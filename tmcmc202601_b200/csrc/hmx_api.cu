@@ -24,6 +24,7 @@
 #include "hmx_mutation.cuh"
 #include "hmx_coop.cuh"
 #include "hmx_legacy.cuh"
+#include "hmx_grad.cuh"
 
 using namespace hmx;
 
@@ -61,6 +62,7 @@ struct hmx_ctx {
     // device scratch
     DevBuf theta, cond_id, pairs, status, iters, trips, logL, obs_state, traj, sig2, x1;
     DevBuf st_in0, st_in1, st_in2, st_out0, st_out1, partial, cs, order, logL_scratch;
+    DevBuf g_traj, g_pull, g_grad, g_dstate;  // hmx_loglik_grad_batch
     DevBuf m_props, m_theta, m_cond, m_inside, m_ll, m_status, m_in_theta, m_in_logL, m_out_theta, m_out_logL, m_groups;  // hmx_mutate
     unsigned long long* d_mut_counts = nullptr;  // [8] accepted, candidates, nonfinite, maxiter, singular
     SchedState* d_sched = nullptr;
@@ -184,6 +186,10 @@ void launch_obs(hmx_ctx* ctx, const ObsParams& P, int blocks) {
     obs_kernel<ALPHA, HILL><<<blocks, 128, 0, ctx->stream>>>(P);
 }
 template <bool ALPHA, int HILL>
+void launch_grad(hmx_ctx* ctx, const GradParams& P, int blocks) {
+    grad_kernel<ALPHA, HILL><<<blocks, 128, 0, ctx->stream>>>(P);
+}
+template <bool ALPHA, int HILL>
 int ode_occupancy() {
     int nb = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ode_kernel<ALPHA, HILL>, kOdeThreads, 0);
@@ -226,7 +232,7 @@ int query_coop_occupancy(hmx_ctx* ctx) {
 // the ODE solve + observation likelihood for one chunk of evaluations already resident on the device
 int run_chunk(hmx_ctx* ctx, const double* d_theta, const int32_t* d_cond, long long N, double* d_logL,
               double* d_obs_state, uint32_t* d_status, uint32_t* d_iters, double* d_traj, bool want_logL,
-              double* d_sigma2 = nullptr, double* d_x1 = nullptr) {
+              double* d_sigma2 = nullptr, double* d_x1 = nullptr, double* d_pull = nullptr) {
     int rc;
     const long long pair_stride = (long long)std::max(ctx->n_obs_max, 1) * kPairStride;
     if ((rc = ensure(ctx, ctx->pairs, (size_t)N * pair_stride * sizeof(double)))) return rc;
@@ -325,6 +331,7 @@ int run_chunk(hmx_ctx* ctx, const double* d_theta, const int32_t* d_cond, long l
         O.obs_stride = (long long)std::max(ctx->n_obs_max, 1) * 12;
         O.sigma2 = d_sigma2;
         O.x1 = d_x1;
+        O.pull = d_pull;
         O.n_cond = ctx->cfg.n_cond;
         const int ob = (int)((N + 127) / 128);
         HMX_DISPATCH(launch_obs, ctx, O, ob);
@@ -490,7 +497,8 @@ void hmx_destroy(hmx_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->theta, &ctx->cond_id, &ctx->pairs, &ctx->status, &ctx->iters, &ctx->trips, &ctx->logL,
                       &ctx->obs_state, &ctx->traj, &ctx->sig2, &ctx->x1, &ctx->st_in0, &ctx->st_in1, &ctx->st_in2, &ctx->st_out0, &ctx->st_out1,
                       &ctx->partial, &ctx->cs, &ctx->order, &ctx->m_props, &ctx->m_theta, &ctx->m_cond, &ctx->m_inside,
-                      &ctx->m_ll, &ctx->m_status, &ctx->m_in_theta, &ctx->m_in_logL, &ctx->m_out_theta, &ctx->m_out_logL, &ctx->row_map, &ctx->m_groups, &ctx->logL_scratch};
+                      &ctx->m_ll, &ctx->m_status, &ctx->m_in_theta, &ctx->m_in_logL, &ctx->m_out_theta, &ctx->m_out_logL, &ctx->row_map, &ctx->m_groups, &ctx->logL_scratch,
+                      &ctx->g_traj, &ctx->g_pull, &ctx->g_grad, &ctx->g_dstate};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     for (void* p : ctx->populations) cudaFree(p);
@@ -584,6 +592,76 @@ int hmx_tsm_obs_rows(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, 
         ll = (double*)ctx->logL_scratch.p;
     }
     return batch_impl(ctx, theta, cond_id, N, ll, x0, status, nullptr, nullptr, sigma2, x1);
+}
+
+int hmx_loglik_grad_batch(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, int64_t N, double* logL, double* grad,
+                          double* dstate, uint32_t* status) {
+    if (!ctx) return HMX_ERR_INVALID;
+    if (N < 0 || (N > 0 && (!theta || !logL || !grad))) return fail(ctx, HMX_ERR_INVALID, "hmx_loglik_grad_batch: NULL argument or N < 0");
+    CU(cudaSetDevice(ctx->device));
+    if (cond_id && N > 0 && !is_device_ptr(cond_id))
+        for (long long i = 0; i < N; ++i)
+            if (cond_id[i] < 0 || cond_id[i] >= ctx->cfg.n_cond) return fail(ctx, HMX_ERR_INVALID, "hmx_loglik_grad_batch: cond_id outside [0, n_cond)");
+    ctx->last_evals = N;
+    ctx->ode_ms_acc = 0.0;
+    ctx->timing_pending = false;
+    CU(cudaMemsetAsync(ctx->d_counters + 1, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    if (N == 0) return HMX_OK;
+    const int nobs = std::max(ctx->n_obs_max, 1);
+    const long long traj_stride = (long long)(ctx->cfg.n_steps + 1) * 12;
+    const long long ds_stride = (long long)nobs * 12 * HMX_NTHETA;
+    // the recursion reads the whole trajectory (240 KB per evaluation at 2500 steps): chunks of <= 4 GiB of it
+    const long long chunk = std::max(1ll, std::min(ctx->chunk_evals, (4ll << 30) / (traj_stride * 8)));
+    int rc;
+    bool need_sync = false;
+    for (long long off = 0; off < N; off += chunk) {
+        const long long n = std::min(chunk, N - off);
+        const void *d_theta, *d_cond;
+        void *d_logL, *h_logL, *d_grad, *h_grad, *d_ds, *h_ds, *d_st, *h_st;
+        if ((rc = stage_in(ctx, theta + off * HMX_NTHETA, (size_t)n * HMX_NTHETA * sizeof(double), ctx->theta, &d_theta))) return rc;
+        if ((rc = stage_in(ctx, cond_id ? cond_id + off : nullptr, (size_t)n * sizeof(int32_t), ctx->cond_id, &d_cond))) return rc;
+        if ((rc = stage_out(ctx, logL + off, (size_t)n * sizeof(double), ctx->logL, &d_logL, &h_logL))) return rc;
+        if ((rc = stage_out(ctx, grad + off * HMX_NTHETA, (size_t)n * HMX_NTHETA * sizeof(double), ctx->g_grad, &d_grad, &h_grad))) return rc;
+        if ((rc = stage_out(ctx, dstate ? dstate + off * ds_stride : nullptr, (size_t)n * ds_stride * sizeof(double), ctx->g_dstate, &d_ds, &h_ds))) return rc;
+        if ((rc = stage_out(ctx, status ? status + off : nullptr, (size_t)n * sizeof(uint32_t), ctx->st_out0, &d_st, &h_st))) return rc;
+        if (!d_st) {
+            if ((rc = ensure(ctx, ctx->status, (size_t)n * sizeof(uint32_t)))) return rc;
+            d_st = ctx->status.p;
+        }
+        if ((rc = ensure(ctx, ctx->g_traj, (size_t)n * traj_stride * sizeof(double)))) return rc;
+        if ((rc = ensure(ctx, ctx->g_pull, (size_t)n * nobs * 5 * sizeof(double)))) return rc;
+        // K1b (trajectory + observation pairs) and K1c (logL, pulls w r / v), then the sensitivity recursion
+        if ((rc = run_chunk(ctx, (const double*)d_theta, (const int32_t*)d_cond, n, (double*)d_logL, nullptr, (uint32_t*)d_st, nullptr,
+                            (double*)ctx->g_traj.p, true, nullptr, nullptr, (double*)ctx->g_pull.p))) return rc;
+        GradParams G;
+        G.K = ctx->K;
+        ThetaMap tm = {HMX_THETA_P, HMX_THETA_Q};
+        G.TM = tm;
+        G.cond = ctx->d_cond;
+        G.theta = (const double*)d_theta;
+        G.cond_id = (const int32_t*)d_cond;
+        G.N = n;
+        G.traj = (const double*)ctx->g_traj.p;
+        G.pull = (const double*)ctx->g_pull.p;
+        G.status = (const uint32_t*)d_st;
+        G.grad = (double*)d_grad;
+        G.dstate = (double*)d_ds;
+        G.n_obs_max = nobs;
+        G.n_cond = ctx->cfg.n_cond;
+        const int blocks = (int)((n * HMX_NTHETA + 127) / 128);
+        HMX_DISPATCH(launch_grad, ctx, G, blocks);
+        CU(cudaGetLastError());
+        ++ctx->launches;
+        if (h_logL) CU(cudaMemcpyAsync(h_logL, d_logL, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (h_grad) CU(cudaMemcpyAsync(h_grad, d_grad, (size_t)n * HMX_NTHETA * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (h_ds) CU(cudaMemcpyAsync(h_ds, d_ds, (size_t)n * ds_stride * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (h_st) CU(cudaMemcpyAsync(h_st, d_st, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        const bool any_host = h_logL || h_grad || h_ds || h_st;
+        need_sync = need_sync || any_host;
+        if (off + chunk < N) CU(cudaStreamSynchronize(ctx->stream));  // trajectory / staging scratch is reused by the next chunk
+    }
+    if (need_sync) CU(cudaStreamSynchronize(ctx->stream));
+    return HMX_OK;
 }
 
 int hmx_trajectory_batch(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, int64_t N, double* g,

@@ -260,6 +260,7 @@ struct ObsParams {
     long long obs_stride;  // n_obs_max * 12
     double* sigma2;        // [N, n_obs_max, 12] or null: TSM variance at the observation rows (S4:1146-1149)
     double* x1;            // [N, n_obs_max, 12, 20] or null: local sensitivities at the observation rows (S4:1150)
+    double* pull;          // [N, n_obs_max, 5] or null: w r / v per observation entry (input of the gradient kernel)
     int n_cond;
 };
 
@@ -276,7 +277,8 @@ __global__ void __launch_bounds__(128) obs_kernel(const __grid_constant__ ObsPar
     const double ll = obs_loglik<ALPHA, HILL>(P.K, C, P.TM, th, P.pairs + w * P.pair_stride, P.status_in[w],
                                               P.obs_state ? P.obs_state + w * P.obs_stride : nullptr, &st,
                                               P.sigma2 ? P.sigma2 + w * P.obs_stride : nullptr,
-                                              P.x1 ? P.x1 + w * P.obs_stride * HMX_NTHETA : nullptr);
+                                              P.x1 ? P.x1 + w * P.obs_stride * HMX_NTHETA : nullptr,
+                                              P.pull ? P.pull + w * (P.obs_stride / 12) * 5 : nullptr);
     const bool okc = cond_valid(P.cond_id, w, P.n_cond);
     P.logL[w] = okc ? ll : -1e20;
     if (P.status_out) P.status_out[w] = okc ? st : (st | kStBadCond);

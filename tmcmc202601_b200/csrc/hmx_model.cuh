@@ -440,8 +440,14 @@ struct RegStash {
 
 // Quasi-Newton direction delta = solve(K, -Q) with K the reference's approximate Jacobian (S5:129-289)
 // evaluated at the point of `e`, computed through the block structure described at the top.
-template <bool ALPHA, int HILL, class AT, class DT, class ST>
-HMX_HD void direction(const SolverConsts& K, const Eval& e, const AT& A, const double (&b)[5], DT& delta, ST& stash) {
+//
+// EXACT = true solves with the TRUE derivative dQ/dg_new instead (same block structure, different 2x2 blocks): what the
+// forward-sensitivity recursion of the likelihood gradient needs (hmx_grad.cuh).  The reference's matrix differs from
+// the derivative in four places: the numerator derivative of the phi barrier (-4 + 8v for -4, S5:185), the constant of
+// the psi barrier derivative (6 for 3, S5:189), an extra -c/eta psi I term in dQ_phi/dphi and a doubled A_ii term on the
+// block diagonals (S5:199-245).  ph0 = clip(phi_0) is only read when EXACT.
+template <bool ALPHA, int HILL, bool EXACT, class AT, class DT, class ST>
+HMX_HD void direction_impl(const SolverConsts& K, const Eval& e, const AT& A, const double (&b)[5], DT& delta, ST& stash, double ph0) {
     double S[5][7];
     double srow[5];  // -c/eta_i h_i: row scaling of the A-derived coefficients C_ij = srow_i A_ij
 #pragma unroll
@@ -461,10 +467,27 @@ HMX_HD void direction(const SolverConsts& K, const Eval& e, const AT& A, const d
         const double aii = hi * A[apk(i, i)];
         const double ap = aii * e.p[i];
         // 2x2 diagonal block of species i (rows i, 6+i; columns i, 6+i), S5:199-245 (+ S5:254-271)
-        const double d00 = e.phip[i] + fma(fma(u, u, K.etaphi_eta[i]), K.inv_dt, u * sd) - ce * u * fma(2.0 * aii, u, e.I[i]);
-        const double d01 = fma(2.0 * u, pd, fma(v, sd, e.p[i] * K.inv_dt)) - ce * fma(3.0, ap, e.I[i]);  // (1/eta) eta = 1
-        const double d10 = fma(u, pd, fma(e.p[i], K.inv_dt, 2.0 * v * sd)) - ce * fma(3.0, ap, 2.0 * e.I[i]);
-        double d11 = e.psip[i] + fma(v, pd, v * v * K.inv_dt) - 2.0 * ce * aii * v * v;
+        double d00, d01, d10, d11;
+        if (!EXACT) {
+            d00 = e.phip[i] + fma(fma(u, u, K.etaphi_eta[i]), K.inv_dt, u * sd) - ce * u * fma(2.0 * aii, u, e.I[i]);
+            d01 = fma(2.0 * u, pd, fma(v, sd, e.p[i] * K.inv_dt)) - ce * fma(3.0, ap, e.I[i]);  // (1/eta) eta = 1
+            d10 = fma(u, pd, fma(e.p[i], K.inv_dt, 2.0 * v * sd)) - ce * fma(3.0, ap, 2.0 * e.I[i]);
+            d11 = e.psip[i] + fma(v, pd, v * v * K.inv_dt) - 2.0 * ce * aii * v * v;
+        } else {
+            // barrier derivatives: d/dv[Kp1(2-4v)/((v-1)^3 v^3)] = 2 Kp1 r^3 (3 s^2 r - 2),
+            //                      d/du[-2Kp1/((u-1)^2 u^3) - 2Kp1/((u-1)^3 u^2)] = 2 Kp1 (10 w + 3) r^4,  w = u(u-1), r = 1/w, s = 2v-1
+            const double wv = fma(v, v, -v), wu = fma(u, u, -u);
+            const double rv = rcp(wv), ru = rcp(wu);
+            const double sv = fma(2.0, v, -1.0);
+            const double phip = (2.0 * K.Kp1) * (rv * rv * rv) * fma(3.0 * sv * sv, rv, -2.0);
+            const double ru2 = ru * ru;
+            const double psip = (2.0 * K.Kp1) * fma(10.0, wu, 3.0) * (ru2 * ru2);
+            // e.I[i] is the gated interaction h_i (A p)_i; the A_ii part of the rank-one term is folded into the block
+            d00 = phip + fma(fma(u, u, K.etaphi_eta[i]), K.inv_dt, u * sd) - ce * aii * u * u;
+            d01 = fma(2.0 * u, pd, fma(v, sd, e.p[i] * K.inv_dt)) - ce * (e.I[i] + ap);
+            d10 = fma(u, pd, fma(e.p[i], K.inv_dt, 2.0 * v * sd)) - ce * (e.I[i] + ap);
+            d11 = psip + fma(v, pd, v * v * K.inv_dt) - ce * aii * v * v;
+        }
         if (ALPHA) d11 += b[i] * K.alpha_eta[i];
         // inverse by Cramer with an fma-compensated determinant
         const double t = d01 * d10;
@@ -516,7 +539,12 @@ HMX_HD void direction(const SolverConsts& K, const Eval& e, const AT& A, const d
         }
     }
     // phi_0 row and the constraint row: S5:222-223, 247
-    const double rK55 = rcp(e.K55);
+    double K55 = e.K55;
+    if (EXACT) {
+        const double r0 = rcp(fma(ph0, ph0, -ph0)), s0 = fma(2.0, ph0, -1.0);
+        K55 = (2.0 * K.Kp1) * (r0 * r0 * r0) * fma(3.0 * s0 * s0, r0, -2.0) + K.inv_dt;
+    }
+    const double rK55 = rcp(K55);
     double sumY1 = 0.0, sumY2 = 0.0;
     double y10[5], y11[5], y20[5], y21[5];
 #pragma unroll
@@ -554,11 +582,23 @@ HMX_HD void direction(const SolverConsts& K, const Eval& e, const AT& A, const d
     delta[11] = dgam;
 }
 
+template <bool ALPHA, int HILL, class AT, class DT, class ST>
+HMX_HD void direction(const SolverConsts& K, const Eval& e, const AT& A, const double (&b)[5], DT& delta, ST& stash) {
+    direction_impl<ALPHA, HILL, false>(K, e, A, b, delta, stash, 0.0);
+}
+
 // convenience overload with a register-array stash (host emulation, observation kernel)
 template <bool ALPHA, int HILL, class AT, class DT>
 HMX_HD void direction(const SolverConsts& K, const Eval& e, const AT& A, const double (&b)[5], DT& delta) {
     RegStash st;
     direction<ALPHA, HILL>(K, e, A, b, delta, st);
+}
+
+// delta = solve(dQ/dg_new, -e.Q) with the exact derivative (ph0 = clip(phi_0) of the point `e` was evaluated at)
+template <bool ALPHA, int HILL, class AT, class DT>
+HMX_HD void direction_exact(const SolverConsts& K, const Eval& e, const AT& A, const double (&b)[5], DT& delta, double ph0) {
+    RegStash st;
+    direction_impl<ALPHA, HILL, true>(K, e, A, b, delta, st, ph0);
 }
 
 }  // namespace hmx

@@ -29,7 +29,7 @@ constexpr int kPairStride = 24;
 template <bool ALPHA, int HILL>
 HMX_HD double obs_loglik(const SolverConsts& K, const CondConsts& C, const ThetaMap& TM, const double* theta,
                          const double* pairs, uint32_t solve_status, double* obs_state, uint32_t* status_out,
-                         double* sig2_out = nullptr, double* x1_out = nullptr) {
+                         double* sig2_out = nullptr, double* x1_out = nullptr, double* pull_out = nullptr) {
     double A[15], b[5];
     theta_to_Ab(theta, A, b);
     bool bad = (solve_status & kStNonfinite) != 0u;
@@ -139,6 +139,7 @@ HMX_HD double obs_loglik(const SolverConsts& K, const CondConsts& C, const Theta
             const double w = C.weights[o * 5 + sp];
             logL -= w * 0.5 * log(2.0 * 3.14159265358979323846 * v);
             logL -= w * 0.5 * (r * r) / v;
+            if (pull_out) pull_out[o * 5 + sp] = w * r / v;  // d logL / d mu at frozen variance (hmx_grad.cuh)
         }
     }
     if (bad) {

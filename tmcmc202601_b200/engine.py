@@ -186,6 +186,21 @@ class HamiltonEngine:
                                                _addr(status)), "hmx_tsm_obs_rows")
         return x0, sig2, x1, logL, status
 
+    def loglik_grad_batch(self, theta, cond_id=None, want_dstate=False):
+        """(logL[N], grad[N,20][, dstate[N,n_obs,12,20]], status[N]): value and gradient of the log-likelihood
+        (hmx_loglik_grad_batch: forward sensitivities with the exact Jacobian, likelihood variance frozen)."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        if theta.ndim != 2 or theta.shape[1] != _abi.NTHETA:
+            raise ValueError("theta must have shape (N, 20)")
+        N = theta.shape[0]
+        cid = None if cond_id is None else np.ascontiguousarray(cond_id, dtype=np.int32)
+        logL, grad = np.empty(N), np.empty((N, _abi.NTHETA))
+        ds = np.zeros((N, self.n_obs_max, _abi.NSTATE, _abi.NTHETA)) if want_dstate else None
+        status = np.zeros(N, dtype=np.uint32)
+        self._check(self._lib.hmx_loglik_grad_batch(self._ctx, _addr(theta), _addr(cid), N, _addr(logL), _addr(grad), _addr(ds), _addr(status)),
+                    "hmx_loglik_grad_batch")
+        return (logL, grad, ds, status) if want_dstate else (logL, grad, status)
+
     def trajectory_batch(self, theta, cond_id=None):
         """g[N, n_steps+1, 12] (hmx_trajectory_batch)."""
         theta = np.ascontiguousarray(theta, dtype=np.float64)
@@ -233,13 +248,13 @@ class HamiltonEngine:
     def legacy_trajectory_rows(self, legacy_cfg: "_abi.HmxLegacyConfig", theta, rows=None):
         """The legacy 4-species solver (hmx_legacy_trajectory_rows): g[N, len(rows) | T+1, 10], status[N], iters[N]."""
         theta = np.ascontiguousarray(theta, dtype=np.float64)
-        nth = 14 if legacy_cfg.n_species == 4 else 20
+        nth = 20 if legacy_cfg.n_species == 5 else 14  # an unsupported n_species is rejected by the library
         if theta.ndim != 2 or theta.shape[1] != nth:
             raise ValueError(f"theta must have shape (N, {nth})")
         N = theta.shape[0]
         r = None if rows is None else np.ascontiguousarray(rows, dtype=np.int32).reshape(-1)
         n_rows = legacy_cfg.n_steps + 1 if r is None else r.size
-        g = np.empty((N, n_rows, 2 * legacy_cfg.n_species + 2))
+        g = np.empty((N, n_rows, 2 * max(legacy_cfg.n_species, 4) + 2))
         status = np.zeros(N, dtype=np.uint32)
         iters = np.zeros(N, dtype=np.uint32)
         self._check(self._lib.hmx_legacy_trajectory_rows(self._ctx, C.byref(legacy_cfg), _addr(theta), N, _addr(r), 0 if r is None else r.size,
