@@ -143,6 +143,23 @@ int hmx_loglik_batch(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, 
 int hmx_tsm_obs_rows(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, int64_t N, double* x0, double* sigma2,
                      double* x1, double* logL, uint32_t* status);
 
+/* replaces: BiofilmTSM.solve_tsm (S4:1077-1160) in FULL: t_arr is arange(n_steps + 1) * dt,
+ *   x0     [N,n_steps+1,12] the deterministic trajectory (may be NULL),
+ *   sigma2 [N,n_steps+1,12] the TSM variance at every time level (level 0 repeats level 1, S4:1139-1141; zeros for conditions
+ *          with tsm_variance = 0),
+ *   status [N] or NULL: HMX_ST_NONFINITE when any entry of x0 or sigma2 is non-finite -- the whole-trajectory test of
+ *          EV:657-667.
+ * Costs about 2.5 solves per evaluation (one residual + n_active direction solves per time level; the reference spends
+ * 98 % of its wall time here) and 480 KB of output per evaluation: for likelihoods use hmx_loglik_batch, which
+ * needs the variance at the observation rows only. */
+int hmx_solve_tsm_batch(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, int64_t N, double* x0, double* sigma2,
+                        uint32_t* status);
+/* EV:657-667 returns -1e20 when sig2 is non-finite at ANY of the T + 1 rows.  hmx_loglik_batch checks the state at every row
+ * and sig2 at the observation rows (all_rows = 0, default: a variance can only blow up off the observation rows, with a finite
+ * state, where the Jacobian is numerically singular); all_rows = 1 evaluates sig2 at every row like the reference (about 2.5x the
+ * cost per evaluation; identical results whenever the guard does not fire). */
+int hmx_set_sig2_guard(hmx_ctx* ctx, int32_t all_rows);
+
 /* replaces: jax.value_and_grad(log_likelihood) as the reference's NUTS / HMC engine consumes it
  * (data_5species/main/tmcmc_nuts_engine.py:202; leapfrog :20-34, tempered_vg :247-249): value and gradient of the
  * log-likelihood of hmx_loglik_batch for a batch of FULL 20-vectors.

@@ -159,3 +159,51 @@ def test_bad_cond_id_is_rejected_not_evaluated_as_condition_zero(built):
         assert np.array_equal(ll.cpu().numpy()[keep], good[keep])
     finally:
         eng.close()
+
+
+@pytest.mark.gpu
+def test_gpu_full_trajectory_variance_and_all_rows_guard(built):
+    """hmx_solve_tsm_batch (BiofilmTSM.solve_tsm in full) against the live reference's sig2 at rows off the observation grid,
+    and the all-rows finiteness guard of EV:657-667 (hmx_set_sig2_guard): same values, same flags as the default."""
+    from tmcmc202601_b200.engine import HamiltonEngine
+    from tmcmc202601_b200.solver import BiofilmNewtonSolver5S
+    from tmcmc202601_b200.tsm import BiofilmTSM
+
+    conds = workloads.load_conditions()
+    for c in CASES[:2] + CASES[-1:]:
+        cd = conds[c["cond"]]
+        solver = BiofilmNewtonSolver5S(phi_init=cd["phi_init"], **c["kw"])
+        tsm = BiofilmTSM(solver, active_theta_indices=c["act"], cov_rel=0.005)
+        t_arr, x0, s2 = tsm.solve_tsm(c["theta"])
+        assert x0.shape == (2501, 12) and s2.shape == (2501, 12) and t_arr.shape == (2501,)
+        rows = np.concatenate([c["idx"], c["extra_rows"]])
+        ref_s2 = np.concatenate([c["sig2"], c["sig2_extra"]])
+        ref_x0 = np.concatenate([c["x0"], c["x0_extra"]])
+        rel = np.abs(s2[rows] - ref_s2) / np.abs(ref_s2)
+        print(f"{c['name']}: full-trajectory sigma2 vs live reference at {len(rows)} rows: max rel {rel.max():.2e}")
+        assert rel.max() < REL and np.abs(x0[rows] - ref_x0).max() <= REL * np.abs(ref_x0).max()
+        assert np.array_equal(s2[0], s2[1])  # x1[0] := x1[1], S4:1139-1141
+        assert np.isfinite(s2).all() and abs(np.abs(s2).max() - c["sig2_all_max"]) <= 1e-9 * c["sig2_all_max"]
+        # rows interface == the reference's _last_x1 rows
+        x0r, s2r, x1r = tsm.solve_tsm_rows(c["theta"], c["extra_rows"])
+        assert _scaled(x1r, c["x1_extra"][:, :, c["act"]]) < REL and np.array_equal(s2r, s2[c["extra_rows"]])
+        tsm.close()
+    # the guard: all rows vs observation rows -- identical values and flags on prior draws (it never fires on finite solves)
+    wl = workloads.four_condition_workload(24, seed=99)
+    eng = HamiltonEngine(wl.config, device=0)
+    try:
+        ll0, st0, _ = eng.loglik_batch(wl.theta, wl.cond_id, return_status=True)
+        eng.set_sig2_guard(True)
+        ll1, st1, _ = eng.loglik_batch(wl.theta, wl.cond_id, return_status=True)
+        assert np.array_equal(ll0, ll1) and np.array_equal(st0, st1)
+        # ... and it does fire where the variance overflows: cov_rel so large that sig2 = inf at every row
+        bad_cfg = workloads.four_condition_workload(2, seed=99).config
+        for k in range(4):
+            bad_cfg.cond[k].cov_rel = 1e200
+        e2 = HamiltonEngine(bad_cfg, device=0)
+        e2.set_sig2_guard(True)
+        llb, stb, _ = e2.loglik_batch(wl.theta[:4], wl.cond_id[:4], return_status=True)
+        assert np.all(llb == -1e20) and np.all(stb & 1)
+        e2.close()
+    finally:
+        eng.close()

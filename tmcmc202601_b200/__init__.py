@@ -1,7 +1,7 @@
 """tmcmc202601_b200 -- B200-native hot path of keisuke58/Tmcmc202601's Stage-1 TMCMC likelihood.
 
 Public surface (names follow the reference):
-    solver.BiofilmNewtonSolver5S
+    solver.BiofilmNewtonSolver5S, solver.BiofilmNewtonSolver (legacy 4-species, alpha_schedule), tsm.BiofilmTSM
     evaluator.LogLikelihoodEvaluator, log_likelihood_sparse, build_species_sigma, build_replicate_sigma,
         build_likelihood_weights, ViscoelasticPrior
     tmcmc.run_TMCMC, run_multi_chain_TMCMC, TMCMCResult, systematic_resample, evaluate_particles_parallel,

@@ -181,7 +181,7 @@ EXPORTS = [
     "hmx_set_timing",
     "hmx_measure_fp64_peak",
     "hmx_mutate", "hmx_mutate_groups", "hmx_trajectory_rows", "hmx_set_latency_kernel", "hmx_cumsum",
-    "hmx_tsm_obs_rows", "hmx_legacy_trajectory_rows", "hmx_loglik_grad_batch",
+    "hmx_tsm_obs_rows", "hmx_legacy_trajectory_rows", "hmx_loglik_grad_batch", "hmx_solve_tsm_batch", "hmx_set_sig2_guard",
     "hmx_population_create", "hmx_population_destroy", "hmx_population_upload", "hmx_population_download",
 ]
 
@@ -319,6 +319,8 @@ def load() -> C.CDLL:
     lib.hmx_population_upload.argtypes = [vp, vp, vp, C.c_int64]
     lib.hmx_population_download.argtypes = [vp, vp, vp, C.c_int64]
     lib.hmx_legacy_trajectory_rows.argtypes = [vp, C.POINTER(HmxLegacyConfig), vp, C.c_int64, vp, C.c_int32, vp, vp, vp]
+    lib.hmx_solve_tsm_batch.argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp]
+    lib.hmx_set_sig2_guard.argtypes = [vp, C.c_int32]
     lib.hmx_loglik_grad_batch.argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp, vp]
     lib.hmx_tsm_obs_rows.argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp]
     lib.hmx_trajectory_rows.argtypes = [vp, vp, vp, C.c_int64, vp, C.c_int32, vp, vp, vp]

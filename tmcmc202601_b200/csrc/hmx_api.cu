@@ -57,6 +57,7 @@ struct hmx_ctx {
     int coop_blocks_per_sm = 1;
     long long coop_max_evals = 0;   // batches up to this size run the 8-lanes-per-solve kernel (HMX_COOP_MAX_EVALS overrides)
     bool last_kernel_coop = false;
+    bool sig2_guard_all = false;  // EV:657-667 on all T + 1 rows instead of the observation rows (hmx_set_sig2_guard)
     std::string err;
 
     // device scratch
@@ -186,6 +187,10 @@ void launch_obs(hmx_ctx* ctx, const ObsParams& P, int blocks) {
     obs_kernel<ALPHA, HILL><<<blocks, 128, 0, ctx->stream>>>(P);
 }
 template <bool ALPHA, int HILL>
+void launch_tsm_rows(hmx_ctx* ctx, const TsmRowsParams& P, long long blocks) {
+    tsm_rows_kernel<ALPHA, HILL><<<(unsigned)blocks, 128, 0, ctx->stream>>>(P);
+}
+template <bool ALPHA, int HILL>
 void launch_grad(hmx_ctx* ctx, const GradParams& P, int blocks) {
     grad_kernel<ALPHA, HILL><<<blocks, 128, 0, ctx->stream>>>(P);
 }
@@ -232,8 +237,14 @@ int query_coop_occupancy(hmx_ctx* ctx) {
 // the ODE solve + observation likelihood for one chunk of evaluations already resident on the device
 int run_chunk(hmx_ctx* ctx, const double* d_theta, const int32_t* d_cond, long long N, double* d_logL,
               double* d_obs_state, uint32_t* d_status, uint32_t* d_iters, double* d_traj, bool want_logL,
-              double* d_sigma2 = nullptr, double* d_x1 = nullptr, double* d_pull = nullptr) {
+              double* d_sigma2 = nullptr, double* d_x1 = nullptr, double* d_pull = nullptr, double* d_sigma2_full = nullptr) {
     int rc;
+    // TSM variance at every time level (hmx_solve_tsm_batch) or the all-rows guard (hmx_set_sig2_guard): needs the trajectory
+    const bool tsm_rows = d_sigma2_full || (ctx->sig2_guard_all && want_logL);
+    if (tsm_rows && !d_traj) {
+        if ((rc = ensure(ctx, ctx->g_traj, (size_t)N * (ctx->cfg.n_steps + 1) * 12 * sizeof(double)))) return rc;
+        d_traj = (double*)ctx->g_traj.p;
+    }
     const long long pair_stride = (long long)std::max(ctx->n_obs_max, 1) * kPairStride;
     if ((rc = ensure(ctx, ctx->pairs, (size_t)N * pair_stride * sizeof(double)))) return rc;
     if ((rc = ensure(ctx, ctx->trips, (size_t)N * sizeof(uint32_t)))) return rc;
@@ -313,6 +324,25 @@ int run_chunk(hmx_ctx* ctx, const double* d_theta, const int32_t* d_cond, long l
     CU(cudaGetLastError());
     ++ctx->launches;
 
+    if (tsm_rows) {
+        if (ctx->cur_row_map) return fail(ctx, HMX_ERR_INVALID, "the all-rows TSM variance needs the full trajectory (no row selection)");
+        TsmRowsParams R;
+        R.K = ctx->K;
+        ThetaMap tmr = {HMX_THETA_P, HMX_THETA_Q};
+        R.TM = tmr;
+        R.cond = ctx->d_cond;
+        R.theta = d_theta;
+        R.cond_id = d_cond;
+        R.N = N;
+        R.traj = d_traj;
+        R.sigma2 = d_sigma2_full;
+        R.status = d_status;
+        R.n_cond = ctx->cfg.n_cond;
+        const long long rb = (N * (long long)ctx->cfg.n_steps + 127) / 128;
+        HMX_DISPATCH(launch_tsm_rows, ctx, R, rb);
+        CU(cudaGetLastError());
+        ++ctx->launches;
+    }
     if (want_logL) {
         ObsParams O;
         O.K = ctx->K;
@@ -365,7 +395,9 @@ int batch_impl(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, long l
     const long long obs_stride = (long long)std::max(ctx->n_obs_max, 1) * 12;
     const long long traj_stride = (long long)(ctx->cur_row_map ? ctx->cur_n_rows : ctx->cfg.n_steps + 1) * 12;
     // trajectories are 100-240 KB per evaluation: keep a chunk's output below ~8 GiB
-    const long long chunk = traj ? std::max(1ll, std::min(ctx->chunk_evals, (8ll << 30) / (traj_stride * 8))) : ctx->chunk_evals;
+    long long chunk = traj ? std::max(1ll, std::min(ctx->chunk_evals, (8ll << 30) / (traj_stride * 8))) : ctx->chunk_evals;
+    if (ctx->sig2_guard_all && !traj)  // the guard keeps a scratch trajectory per chunk
+        chunk = std::max(1ll, std::min(chunk, (4ll << 30) / ((long long)(ctx->cfg.n_steps + 1) * 12 * 8)));
     bool need_sync = false;
     for (long long off = 0; off < N; off += chunk) {
         const long long n = std::min(chunk, N - off);
@@ -592,6 +624,50 @@ int hmx_tsm_obs_rows(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, 
         ll = (double*)ctx->logL_scratch.p;
     }
     return batch_impl(ctx, theta, cond_id, N, ll, x0, status, nullptr, nullptr, sigma2, x1);
+}
+
+int hmx_set_sig2_guard(hmx_ctx* ctx, int32_t all_rows) {
+    if (!ctx) return HMX_ERR_INVALID;
+    ctx->sig2_guard_all = all_rows != 0;
+    return HMX_OK;
+}
+
+int hmx_solve_tsm_batch(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, int64_t N, double* x0, double* sigma2,
+                        uint32_t* status) {
+    if (!ctx) return HMX_ERR_INVALID;
+    if (N < 0 || (N > 0 && (!theta || !sigma2))) return fail(ctx, HMX_ERR_INVALID, "hmx_solve_tsm_batch: NULL argument or N < 0");
+    CU(cudaSetDevice(ctx->device));
+    if (cond_id && N > 0 && !is_device_ptr(cond_id))
+        for (long long i = 0; i < N; ++i)
+            if (cond_id[i] < 0 || cond_id[i] >= ctx->cfg.n_cond) return fail(ctx, HMX_ERR_INVALID, "hmx_solve_tsm_batch: cond_id outside [0, n_cond)");
+    ctx->last_evals = N;
+    ctx->ode_ms_acc = 0.0;
+    ctx->timing_pending = false;
+    CU(cudaMemsetAsync(ctx->d_counters + 1, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    if (N == 0) return HMX_OK;
+    const long long stride = (long long)(ctx->cfg.n_steps + 1) * 12;
+    const long long chunk = std::max(1ll, std::min(ctx->chunk_evals, (4ll << 30) / (stride * 8)));
+    int rc;
+    bool need_sync = false;
+    for (long long off = 0; off < N; off += chunk) {
+        const long long n = std::min(chunk, N - off);
+        const void *d_theta, *d_cond;
+        void *d_x0, *h_x0, *d_s2, *h_s2, *d_st, *h_st;
+        if ((rc = stage_in(ctx, theta + off * HMX_NTHETA, (size_t)n * HMX_NTHETA * sizeof(double), ctx->theta, &d_theta))) return rc;
+        if ((rc = stage_in(ctx, cond_id ? cond_id + off : nullptr, (size_t)n * sizeof(int32_t), ctx->cond_id, &d_cond))) return rc;
+        if ((rc = stage_out(ctx, x0 ? x0 + off * stride : nullptr, (size_t)n * stride * sizeof(double), ctx->traj, &d_x0, &h_x0))) return rc;
+        if ((rc = stage_out(ctx, sigma2 + off * stride, (size_t)n * stride * sizeof(double), ctx->g_dstate, &d_s2, &h_s2))) return rc;
+        if ((rc = stage_out(ctx, status ? status + off : nullptr, (size_t)n * sizeof(uint32_t), ctx->st_out0, &d_st, &h_st))) return rc;
+        if ((rc = run_chunk(ctx, (const double*)d_theta, (const int32_t*)d_cond, n, nullptr, nullptr, (uint32_t*)d_st, nullptr, (double*)d_x0,
+                            false, nullptr, nullptr, nullptr, (double*)d_s2))) return rc;
+        if (h_x0) CU(cudaMemcpyAsync(h_x0, d_x0, (size_t)n * stride * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (h_s2) CU(cudaMemcpyAsync(h_s2, d_s2, (size_t)n * stride * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (h_st) CU(cudaMemcpyAsync(h_st, d_st, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        need_sync = need_sync || h_x0 || h_s2 || h_st;
+        if (off + chunk < N) CU(cudaStreamSynchronize(ctx->stream));
+    }
+    if (need_sync) CU(cudaStreamSynchronize(ctx->stream));
+    return HMX_OK;
 }
 
 int hmx_loglik_grad_batch(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, int64_t N, double* logL, double* grad,

@@ -284,6 +284,61 @@ __global__ void __launch_bounds__(128) obs_kernel(const __grid_constant__ ObsPar
     if (P.status_out) P.status_out[w] = okc ? st : (st | kStBadCond);
 }
 
+// ---- TSM variance at EVERY time level (BiofilmTSM.solve_tsm in full, S4:1095-1160) -------------------------------------
+// One thread per (evaluation, time level t >= 1) on a stored trajectory: sigma2[t] from (g_t, g_{t-1}); level 0 repeats
+// level 1 (S4:1139-1141).  Used by hmx_solve_tsm_batch and by the all-rows finiteness guard (EV:657-667 scans sig2 at all
+// T + 1 rows, hmx_set_sig2_guard).  ~(1 residual + n_active directions) per level: ~1.5x the cost of the solve itself.
+struct TsmRowsParams {
+    SolverConsts K;
+    ThetaMap TM;
+    const CondConsts* cond;
+    const double* theta;
+    const int32_t* cond_id;
+    long long N;
+    const double* traj;  // [N, n_steps + 1, 12]
+    double* sigma2;      // [N, n_steps + 1, 12] or null (guard only)
+    uint32_t* status;    // [N]: kStNonfinite is OR-ed in when a variance (or a state) is non-finite
+    int n_cond;
+};
+
+template <bool ALPHA, int HILL>
+__global__ void __launch_bounds__(128) tsm_rows_kernel(const __grid_constant__ TsmRowsParams P) {
+    const int T = P.K.n_steps;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long w = tid / T;
+    const int t = (int)(tid - w * T) + 1;
+    if (w >= P.N) return;
+    const CondConsts& C = P.cond[cond_index(P.cond_id, w, P.n_cond)];
+    double th[HMX_NTHETA], A[15], b[5], x[12], gp[11], sig2[12], covp[5];
+#pragma unroll
+    for (int k = 0; k < HMX_NTHETA; ++k) th[k] = __ldg(P.theta + w * HMX_NTHETA + k);
+    theta_to_Ab(th, A, b);
+    const double* tr = P.traj + (w * (long long)(T + 1) + t) * 12;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) x[i] = tr[i];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) gp[i] = tr[i - 12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) sig2[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) covp[i] = 0.0;
+    bool ok = true;
+    if (C.tsm_variance) ok = tsm_row<ALPHA, HILL>(P.K, C, P.TM, th, A, b, x, gp, sig2, covp, nullptr);
+    double chk = 0.0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) chk = fma(x[i], 0.0, chk);
+    if (!ok || chk != 0.0) atomicOr(P.status + w, kStNonfinite);
+    if (P.sigma2) {
+        double* out = P.sigma2 + (w * (long long)(T + 1) + t) * 12;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) out[i] = sig2[i];
+        if (t == 1) {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) out[i - 12] = sig2[i];
+        }
+    }
+}
+
 // ---- FP64 peak: 8 independent DFMA chains per thread, operands in registers ---------------------------
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;

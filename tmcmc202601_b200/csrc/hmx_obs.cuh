@@ -26,6 +26,66 @@ struct ThetaMap {
 // pair = [g_t (12), phi_old(5), phi0_old, psi_old(5), pad] for t = max(idx,1); 24 doubles per observation row
 constexpr int kPairStride = 24;
 
+// TSM variance of ONE trajectory row (S4:1095-1150): x = g_t, gp = g_{t-1} (first 11 entries).  sig2[12] receives
+// sum_k x1_k^2 (cov_rel theta_k)^2 + 1e-12, covp[5] the phi/psi (or phi/gamma) covariance sums of EV:723-740, x1_out
+// (optional, [12,20] row-major, pre-zeroed by the caller) the sensitivities.  Returns false when a variance is non-finite.
+template <bool ALPHA, int HILL>
+HMX_HD bool tsm_row(const SolverConsts& K, const CondConsts& C, const ThetaMap& TM, const double* theta, const double (&A)[15],
+                    const double (&b)[5], const double (&x)[12], const double (&gp)[11], double (&sig2)[12], double (&covp)[5],
+                    double* x1_out) {
+    bool ok = true;
+    Eval e;
+    residual<ALPHA, HILL>(K, x, gp, A, b, e);  // clipped copies, as compute_Jacobian_matrix does (S5:734-758)
+    for (int k = 0; k < HMX_NTHETA; ++k) {
+        if (!((C.active_theta_mask >> k) & 1u)) continue;
+        const int p = TM.p[k], q = TM.q[k];
+        const double tk = C.cov_rel * theta[k];
+        const double var_k = tk * tk;  // S4:1144
+#pragma unroll
+        for (int i = 0; i < 12; ++i) e.Q[i] = 0.0;
+        if (q < 0) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i)
+                if (i == p) e.Q[6 + i] = K.alpha_eta[i] * e.ps[i];
+        } else {
+            double pq = 0.0, pp = 0.0;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                pq = (i == q) ? e.p[i] : pq;
+                pp = (i == p) ? e.p[i] : pp;
+            }
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const double hi = (HILL != 0 && i == 4) ? e.h : 1.0;
+                double rho = 0.0;
+                if (i == p) rho += K.c_eta[i] * hi * pq;
+                if (i == q && p != q) rho += K.c_eta[i] * hi * pp;
+                e.Q[i] = -rho * e.ps[i];
+                e.Q[6 + i] = -rho * e.ph[i];
+            }
+        }
+        double x1[12];
+        direction<ALPHA, HILL>(K, e, A, b, x1);
+        if (x1_out) {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) x1_out[(size_t)i * HMX_NTHETA + k] = x1[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 12; ++i) sig2[i] = fma(x1[i] * x1[i], var_k, sig2[i]);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const double xo = C.use_absolute_volume ? x1[11] : x1[6 + i];
+            covp[i] = fma(x1[i] * xo, var_k, covp[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        sig2[i] += 1e-12;  // S4:324-332
+        if (!(fabs(sig2[i]) <= 1.79e308)) ok = false;
+    }
+    return ok;
+}
+
 template <bool ALPHA, int HILL>
 HMX_HD double obs_loglik(const SolverConsts& K, const CondConsts& C, const ThetaMap& TM, const double* theta,
                          const double* pairs, uint32_t solve_status, double* obs_state, uint32_t* status_out,
@@ -61,55 +121,7 @@ HMX_HD double obs_loglik(const SolverConsts& K, const CondConsts& C, const Theta
             for (int i = 0; i < 12 * HMX_NTHETA; ++i) x1_out[(size_t)o * 12 * HMX_NTHETA + i] = 0.0;
         }
         if (C.tsm_variance) {
-            Eval e;
-            residual<ALPHA, HILL>(K, x, gp, A, b, e);  // clipped copies, as compute_Jacobian_matrix does (S5:734-758)
-            for (int k = 0; k < HMX_NTHETA; ++k) {
-                if (!((C.active_theta_mask >> k) & 1u)) continue;
-                const int p = TM.p[k], q = TM.q[k];
-                const double tk = C.cov_rel * theta[k];
-                const double var_k = tk * tk;  // S4:1144
-#pragma unroll
-                for (int i = 0; i < 12; ++i) e.Q[i] = 0.0;
-                if (q < 0) {
-#pragma unroll
-                    for (int i = 0; i < 5; ++i)
-                        if (i == p) e.Q[6 + i] = K.alpha_eta[i] * e.ps[i];
-                } else {
-                    double pq = 0.0, pp = 0.0;
-#pragma unroll
-                    for (int i = 0; i < 5; ++i) {
-                        pq = (i == q) ? e.p[i] : pq;
-                        pp = (i == p) ? e.p[i] : pp;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 5; ++i) {
-                        const double hi = (HILL != 0 && i == 4) ? e.h : 1.0;
-                        double rho = 0.0;
-                        if (i == p) rho += K.c_eta[i] * hi * pq;
-                        if (i == q && p != q) rho += K.c_eta[i] * hi * pp;
-                        e.Q[i] = -rho * e.ps[i];
-                        e.Q[6 + i] = -rho * e.ph[i];
-                    }
-                }
-                double x1[12];
-                direction<ALPHA, HILL>(K, e, A, b, x1);
-                if (x1_out) {
-#pragma unroll
-                    for (int i = 0; i < 12; ++i) x1_out[((size_t)o * 12 + i) * HMX_NTHETA + k] = x1[i];
-                }
-#pragma unroll
-                for (int i = 0; i < 12; ++i) sig2[i] = fma(x1[i] * x1[i], var_k, sig2[i]);
-#pragma unroll
-                for (int i = 0; i < 5; ++i) {
-                    const double xo = C.use_absolute_volume ? x1[11] : x1[6 + i];
-                    covp[i] = fma(x1[i] * xo, var_k, covp[i]);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 12; ++i) {
-                sig2[i] += 1e-12;  // S4:324-332
-                if (!(fabs(sig2[i]) <= 1.79e308)) bad = true;
-            }
+            if (!tsm_row<ALPHA, HILL>(K, C, TM, theta, A, b, x, gp, sig2, covp, x1_out ? x1_out + (size_t)o * 12 * HMX_NTHETA : nullptr)) bad = true;
         }
         if (sig2_out) {  // sigma2[idx] of solve_tsm (S4:1146-1149); zeros on the np.allclose short-cut (TSMA:366-401)
 #pragma unroll

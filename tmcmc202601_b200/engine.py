@@ -186,6 +186,23 @@ class HamiltonEngine:
                                                _addr(status)), "hmx_tsm_obs_rows")
         return x0, sig2, x1, logL, status
 
+    def solve_tsm_batch(self, theta, cond_id=None, want_x0=True):
+        """BiofilmTSM.solve_tsm in full (hmx_solve_tsm_batch): x0[N,T+1,12] (or None), sigma2[N,T+1,12], status[N]."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        if theta.ndim != 2 or theta.shape[1] != _abi.NTHETA:
+            raise ValueError("theta must have shape (N, 20)")
+        N = theta.shape[0]
+        cid = None if cond_id is None else np.ascontiguousarray(cond_id, dtype=np.int32)
+        x0 = np.empty((N, self.n_steps + 1, _abi.NSTATE)) if want_x0 else None
+        s2 = np.empty((N, self.n_steps + 1, _abi.NSTATE))
+        status = np.zeros(N, dtype=np.uint32)
+        self._check(self._lib.hmx_solve_tsm_batch(self._ctx, _addr(theta), _addr(cid), N, _addr(x0), _addr(s2), _addr(status)), "hmx_solve_tsm_batch")
+        return x0, s2, status
+
+    def set_sig2_guard(self, all_rows: bool):
+        """EV:657-667 at all T + 1 rows (True: the reference's scan, ~2.5x the cost) or at the observation rows (False, default)."""
+        self._check(self._lib.hmx_set_sig2_guard(self._ctx, int(bool(all_rows))), "hmx_set_sig2_guard")
+
     def loglik_grad_batch(self, theta, cond_id=None, want_dstate=False):
         """(logL[N], grad[N,20][, dstate[N,n_obs,12,20]], status[N]): value and gradient of the log-likelihood
         (hmx_loglik_grad_batch: forward sensitivities with the exact Jacobian, likelihood variance frozen)."""

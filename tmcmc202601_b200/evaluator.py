@@ -97,7 +97,7 @@ class LogLikelihoodEvaluator:
                  rho: float = 0.0, theta_linearization: Optional[np.ndarray] = None, use_analytical: bool = True,
                  paper_mode: bool = False, debug_logger=None, use_absolute_volume: bool = False,
                  weights: Optional[np.ndarray] = None, device: int = 0, tsm_variance: bool = True,
-                 strict_mapping: bool = False, engine_factory=None, latency_kernel: bool = False):
+                 strict_mapping: bool = False, engine_factory=None, latency_kernel: bool = False, sig2_guard_all_rows: bool = False):
         if abs(rho) > 1e-9:
             raise NotImplementedError("rho != 0 is never used by the reference (MAIN:2221)")
         self.active_species = list(active_species)
@@ -145,6 +145,9 @@ class LogLikelihoodEvaluator:
         # engine_factory is the test seam (CPU suite injects an oracle-backed stand-in); the product default is the GPU
         make_engine = engine_factory or (lambda cfg: HamiltonEngine(cfg, device=self.device))
         self._engine = make_engine(_abi.make_config(conds, active_species=self.active_species, **kw))
+        if sig2_guard_all_rows and hasattr(self._engine, "set_sig2_guard"):
+            # EV:657-667 scans sig2 at all T + 1 rows; the default checks the state at every row and sig2 at the observation rows
+            self._engine.set_sig2_guard(True)
         if latency_kernel and hasattr(self._engine, "set_latency_kernel"):
             self._engine.set_latency_kernel(-1)  # K1L for production-sized launches (see include/hmx.h)
 
