@@ -10,6 +10,7 @@
 #include "../../tmcmc202601_b200/csrc/hmx_obs.cuh"
 #include "../../tmcmc202601_b200/csrc/hmx_mutation.cuh"
 #include "../../tmcmc202601_b200/csrc/hmx_grad.cuh"
+#include "../../tmcmc202601_b200/csrc/hmx_dense.cuh"
 
 using namespace hmx;
 
@@ -124,7 +125,39 @@ static void emu_sens(const SolverConsts& K, const double* theta, const double* g
     }
 }
 
+template <bool ALPHA, int HILL>
+static void run_reference_loop(const SolverConsts& K, const CondConsts& C, const double* theta, double* g_arr, uint32_t* status, uint32_t* iters) {
+    uint32_t st = 0, it = 0, tr = 0;
+    memcpy(g_arr, C.g0, 12 * sizeof(double));
+    reference_loop_solve<ALPHA, HILL>(K, theta, C.g0, st, it, tr, [&](const double (&g)[12], const RegArr<11>&, int step) {
+        memcpy(g_arr + (size_t)(step + 1) * 12, g, 12 * sizeof(double));
+    });
+    *status = st;
+    *iters = it;
+}
+
 extern "C" {
+
+// hmx_dense.cuh on the CPU: the reference's loop nest with the dense pivoted solve + ridge retry; g_arr [(n_steps + 1), 12]
+int emu_reference_loop(const hmx_config* cfg, int cond, const double* theta, double* g_arr, uint32_t* status, uint32_t* iters) {
+    SolverConsts K;
+    CondConsts C;
+    make_solver_consts(*cfg, K);
+    make_cond_consts(*cfg, cond, C);
+    const bool alpha = cfg->alpha_const != 0.0;
+    const int hill = hill_variant(K);
+    if (alpha) {
+        if (hill == 0) run_reference_loop<true, 0>(K, C, theta, g_arr, status, iters);
+        else if (hill == 1) run_reference_loop<true, 1>(K, C, theta, g_arr, status, iters);
+        else run_reference_loop<true, 2>(K, C, theta, g_arr, status, iters);
+    } else {
+        if (hill == 0) run_reference_loop<false, 0>(K, C, theta, g_arr, status, iters);
+        else if (hill == 1) run_reference_loop<false, 1>(K, C, theta, g_arr, status, iters);
+        else run_reference_loop<false, 2>(K, C, theta, g_arr, status, iters);
+    }
+    return 0;
+}
+
 
 // the generic NS-species solver (hmx_legacy.cuh) on the CPU: g_arr [(n_steps + 1), 2 NS + 2]
 int emu_legacy_solve(const hmx_legacy_config* cfg, const double* theta, double* g_arr, uint32_t* status, uint32_t* iters) {

@@ -57,6 +57,7 @@ struct hmx_ctx {
     int coop_blocks_per_sm = 1;
     long long coop_max_evals = 0;   // batches up to this size run the 8-lanes-per-solve kernel (HMX_COOP_MAX_EVALS overrides)
     bool last_kernel_coop = false;
+    bool force_reference_loop = false;  // HMX_FORCE_REFERENCE_LOOP=1: every evaluation goes through K1r (cross-check / tests)
     bool sig2_guard_all = false;  // EV:657-667 on all T + 1 rows instead of the observation rows (hmx_set_sig2_guard)
     std::string err;
 
@@ -171,6 +172,10 @@ int red_blocks(long long N) {
 template <bool ALPHA, int HILL>
 void launch_ode(hmx_ctx* ctx, const OdeParams& P, int blocks) {
     ode_kernel<ALPHA, HILL><<<blocks, kOdeThreads, 0, ctx->stream>>>(P);
+}
+template <bool ALPHA, int HILL>
+void launch_resolve(hmx_ctx* ctx, const OdeParams& P, int blocks, int force) {
+    resolve_kernel<ALPHA, HILL><<<blocks, 128, 0, ctx->stream>>>(P, force);
 }
 template <bool ALPHA, int HILL>
 void launch_coop(hmx_ctx* ctx, const OdeParams& P, int blocks) {
@@ -321,6 +326,10 @@ int run_chunk(hmx_ctx* ctx, const double* d_theta, const int32_t* d_cond, long l
         ctx->timing_pending = true;
     }
     sched_update_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_sched, ctx->d_counters + 4, ctx->d_counters + 12, ctx->cfg.n_cond);
+    CU(cudaGetLastError());
+    ++ctx->launches;
+    // K1r: evaluations flagged HMX_ST_SINGULAR are solved again with the dense, pivoted solve + ridge retry (hmx_dense.cuh)
+    HMX_DISPATCH(launch_resolve, ctx, P, (int)((N + 127) / 128), ctx->force_reference_loop ? 1 : 0);
     CU(cudaGetLastError());
     ++ctx->launches;
 
@@ -514,6 +523,7 @@ int hmx_create(hmx_ctx** out, const hmx_config* cfg, int32_t device) {
     // guarantees "merged launches == separate launches" and "sharded == single GPU" (both bitwise) would go.
     ctx->coop_max_evals = 0;
     if (const char* cm = getenv("HMX_COOP_MAX_EVALS")) ctx->coop_max_evals = atoll(cm);
+    if (const char* fr = getenv("HMX_FORCE_REFERENCE_LOOP")) ctx->force_reference_loop = atoi(fr) != 0;
     if (const char* ce = getenv("HMX_CHUNK_EVALS")) {
         const long long v = atoll(ce);
         if (v > 0) ctx->chunk_evals = v;

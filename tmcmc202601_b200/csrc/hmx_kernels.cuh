@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include "hmx_obs.cuh"
+#include "hmx_dense.cuh"
 
 namespace hmx {
 
@@ -168,6 +169,45 @@ __global__ void HMX_ODE_BOUNDS ode_kernel(const __grid_constant__ OdeParams P) {
             have = false;
         }
     }
+}
+
+// K1r: evaluations flagged HMX_ST_SINGULAR by the production kernel are solved again from their initial state with the
+// reference's loop nest and a dense, pivoted linear solve incl. the 1e-10 ridge retry (hmx_dense.cuh).  One thread per
+// evaluation; threads of unflagged evaluations return at once (force != 0: every evaluation, a test / cross-check mode).
+template <bool ALPHA, int HILL>
+__global__ void __launch_bounds__(128) resolve_kernel(const __grid_constant__ OdeParams P, int force) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= P.N) return;
+    if (!force && !(P.status[w] & kStSingular)) return;
+    const int c = cond_index(P.cond_id, w, P.n_cond);
+    const OdeCond& oc = P.cond[c];
+    double th[HMX_NTHETA];
+    for (int k = 0; k < HMX_NTHETA; ++k) th[k] = P.theta[w * HMX_NTHETA + k];
+    if (P.traj) {
+        const int r0 = P.traj_row_map ? P.traj_row_map[0] : 0;
+        if (r0 >= 0)
+            for (int i = 0; i < 12; ++i) P.traj[(w * (long long)P.traj_n_rows + r0) * 12 + i] = oc.g0[i];
+    }
+    int next_obs = 0;
+    auto step_end = [&](const double (&g)[12], const RegArr<11>& gp, int step_idx) {
+        while (next_obs < oc.n_obs && max(oc.idx[next_obs], 1) == step_idx + 1) {
+            double* q = P.pairs + w * P.pair_stride + next_obs * kPairStride;
+            for (int i = 0; i < 12; ++i) q[i] = g[i];
+            for (int i = 0; i < 11; ++i) q[12 + i] = gp[i];
+            q[23] = 0.0;
+            ++next_obs;
+        }
+        if (P.traj) {
+            const int r = P.traj_row_map ? P.traj_row_map[step_idx + 1] : step_idx + 1;
+            if (r >= 0)
+                for (int i = 0; i < 12; ++i) P.traj[(w * (long long)P.traj_n_rows + r) * 12 + i] = g[i];
+        }
+    };
+    uint32_t st = 0u, its = 0u, trips = 0u;
+    reference_loop_solve<ALPHA, HILL>(P.K, th, oc.g0, st, its, trips, step_end);
+    P.status[w] = st;
+    P.iters[w] = its;
+    P.trips[w] = trips;
 }
 
 // ---- cost-ordered work list ---------------------------------------------------------------------------

@@ -438,6 +438,39 @@ struct RegStash {
     HMX_HD double& operator[](int k) { return v[k]; }
 };
 
+// 2x2 diagonal block of species i (rows i, 6+i; columns i, 6+i) of the reference's Newton matrix, S5:199-245 (+ S5:254-271),
+// or -- EXACT -- of the true derivative dQ/dg_new.
+template <bool ALPHA, int HILL, bool EXACT, class AT>
+HMX_HD void block2x2(const SolverConsts& K, const Eval& e, const AT& A, const double (&b)[5], int i, double& d00, double& d01,
+                     double& d10, double& d11) {
+        const double v = e.ph[i], u = e.ps[i], pd = e.phd[i], sd = e.psd[i];
+        const double ce = K.c_eta[i];
+        const double hi = (HILL != 0 && i == 4) ? e.h : 1.0;
+        const double aii = hi * A[apk(i, i)];
+        const double ap = aii * e.p[i];
+        if (!EXACT) {
+            d00 = e.phip[i] + fma(fma(u, u, K.etaphi_eta[i]), K.inv_dt, u * sd) - ce * u * fma(2.0 * aii, u, e.I[i]);
+            d01 = fma(2.0 * u, pd, fma(v, sd, e.p[i] * K.inv_dt)) - ce * fma(3.0, ap, e.I[i]);  // (1/eta) eta = 1
+            d10 = fma(u, pd, fma(e.p[i], K.inv_dt, 2.0 * v * sd)) - ce * fma(3.0, ap, 2.0 * e.I[i]);
+            d11 = e.psip[i] + fma(v, pd, v * v * K.inv_dt) - 2.0 * ce * aii * v * v;
+        } else {
+            // barrier derivatives: d/dv[Kp1(2-4v)/((v-1)^3 v^3)] = 2 Kp1 r^3 (3 s^2 r - 2),
+            //                      d/du[-2Kp1/((u-1)^2 u^3) - 2Kp1/((u-1)^3 u^2)] = 2 Kp1 (10 w + 3) r^4,  w = u(u-1), r = 1/w, s = 2v-1
+            const double wv = fma(v, v, -v), wu = fma(u, u, -u);
+            const double rv = rcp(wv), ru = rcp(wu);
+            const double sv = fma(2.0, v, -1.0);
+            const double phip = (2.0 * K.Kp1) * (rv * rv * rv) * fma(3.0 * sv * sv, rv, -2.0);
+            const double ru2 = ru * ru;
+            const double psip = (2.0 * K.Kp1) * fma(10.0, wu, 3.0) * (ru2 * ru2);
+            // e.I[i] is the gated interaction h_i (A p)_i; the A_ii part of the rank-one term is folded into the block
+            d00 = phip + fma(fma(u, u, K.etaphi_eta[i]), K.inv_dt, u * sd) - ce * aii * u * u;
+            d01 = fma(2.0 * u, pd, fma(v, sd, e.p[i] * K.inv_dt)) - ce * (e.I[i] + ap);
+            d10 = fma(u, pd, fma(e.p[i], K.inv_dt, 2.0 * v * sd)) - ce * (e.I[i] + ap);
+            d11 = psip + fma(v, pd, v * v * K.inv_dt) - ce * aii * v * v;
+        }
+        if (ALPHA) d11 += b[i] * K.alpha_eta[i];
+}
+
 // Quasi-Newton direction delta = solve(K, -Q) with K the reference's approximate Jacobian (S5:129-289)
 // evaluated at the point of `e`, computed through the block structure described at the top.
 //
@@ -468,27 +501,7 @@ HMX_HD void direction_impl(const SolverConsts& K, const Eval& e, const AT& A, co
         const double ap = aii * e.p[i];
         // 2x2 diagonal block of species i (rows i, 6+i; columns i, 6+i), S5:199-245 (+ S5:254-271)
         double d00, d01, d10, d11;
-        if (!EXACT) {
-            d00 = e.phip[i] + fma(fma(u, u, K.etaphi_eta[i]), K.inv_dt, u * sd) - ce * u * fma(2.0 * aii, u, e.I[i]);
-            d01 = fma(2.0 * u, pd, fma(v, sd, e.p[i] * K.inv_dt)) - ce * fma(3.0, ap, e.I[i]);  // (1/eta) eta = 1
-            d10 = fma(u, pd, fma(e.p[i], K.inv_dt, 2.0 * v * sd)) - ce * fma(3.0, ap, 2.0 * e.I[i]);
-            d11 = e.psip[i] + fma(v, pd, v * v * K.inv_dt) - 2.0 * ce * aii * v * v;
-        } else {
-            // barrier derivatives: d/dv[Kp1(2-4v)/((v-1)^3 v^3)] = 2 Kp1 r^3 (3 s^2 r - 2),
-            //                      d/du[-2Kp1/((u-1)^2 u^3) - 2Kp1/((u-1)^3 u^2)] = 2 Kp1 (10 w + 3) r^4,  w = u(u-1), r = 1/w, s = 2v-1
-            const double wv = fma(v, v, -v), wu = fma(u, u, -u);
-            const double rv = rcp(wv), ru = rcp(wu);
-            const double sv = fma(2.0, v, -1.0);
-            const double phip = (2.0 * K.Kp1) * (rv * rv * rv) * fma(3.0 * sv * sv, rv, -2.0);
-            const double ru2 = ru * ru;
-            const double psip = (2.0 * K.Kp1) * fma(10.0, wu, 3.0) * (ru2 * ru2);
-            // e.I[i] is the gated interaction h_i (A p)_i; the A_ii part of the rank-one term is folded into the block
-            d00 = phip + fma(fma(u, u, K.etaphi_eta[i]), K.inv_dt, u * sd) - ce * aii * u * u;
-            d01 = fma(2.0 * u, pd, fma(v, sd, e.p[i] * K.inv_dt)) - ce * (e.I[i] + ap);
-            d10 = fma(u, pd, fma(e.p[i], K.inv_dt, 2.0 * v * sd)) - ce * (e.I[i] + ap);
-            d11 = psip + fma(v, pd, v * v * K.inv_dt) - ce * aii * v * v;
-        }
-        if (ALPHA) d11 += b[i] * K.alpha_eta[i];
+        block2x2<ALPHA, HILL, EXACT>(K, e, A, b, i, d00, d01, d10, d11);
         // inverse by Cramer with an fma-compensated determinant
         const double t = d01 * d10;
         const double det = fma(d00, d11, -t) + fma(-d01, d10, t);
