@@ -140,6 +140,12 @@ def test_cumsum_equals_numpy_chain_bitwise_on_adversarial_weights(eng):
     cases["single"] = np.array([1.0])
     w = rng.random(2_000_000)
     cases["two_million"] = w / w.sum()
+    # running sum lands exactly on / next to a power of two at tile boundaries: the multi-CTA path's binade guess (made from
+    # a differently associated sum) is wrong there and the tile must fall back to the chain
+    cases["boundary_exact"] = np.concatenate([np.full(4096, 0.25 / 4096), np.full(4096, 0.25 / 4096), np.full(8192, 0.5 / 8192)])
+    cases["boundary_near"] = np.concatenate([np.full(4096, 0.125 / 4096 * (1 - 2.0 ** -50)), np.full(4096 * 7, 0.875 / (4096 * 7))])
+    w = np.exp(rng.normal(size=1_500_000) * 12)
+    cases["tempered_heavy_tail"] = w / w.sum()
     for name, w in cases.items():
         w = np.ascontiguousarray(w, dtype=np.float64)
         ref = np.cumsum(w)
@@ -147,10 +153,33 @@ def test_cumsum_equals_numpy_chain_bitwise_on_adversarial_weights(eng):
         got = eng.cumsum(w)
         assert np.array_equal(got.view(np.uint64), ref.view(np.uint64)), name
     # and the resampling indices that depend on it
-    for name in ("uniform", "lognormal", "ties", "two_million"):
+    for name in ("uniform", "lognormal", "ties", "two_million", "tempered_heavy_tail"):
         w = cases[name] / cases[name].sum()
         u = float(rng.random())
         cs = np.cumsum(w)
         cs[-1] = 1.0
         want = np.clip(np.searchsorted(cs, (u + np.arange(len(w))) / len(w)), 0, len(w) - 1)
         assert np.array_equal(eng.resample(w, u), want), name
+
+
+def test_multi_cta_cumsum_equals_single_cta_kernel(built, monkeypatch):
+    """The multi-CTA cumulative sum (tiles in parallel, integer prefix of the tile totals inside a binade) against the
+    single-CTA kernel it replaces for large N: identical bits on 20 random weight vectors of ragged length."""
+    from tmcmc202601_b200 import _abi
+    from tmcmc202601_b200.engine import HamiltonEngine
+
+    cond = _abi.make_cond(np.zeros((0, 5)), [], 1.0, 0.2, tsm_variance=False)
+    multi = HamiltonEngine(_abi.make_config([cond]), device=0)
+    monkeypatch.setenv("HMX_CUMSUM_SINGLE_CTA", "1")
+    single = HamiltonEngine(_abi.make_config([cond]), device=0)
+    try:
+        rng = np.random.default_rng(7)
+        for k in range(20):
+            n = int(rng.integers(4 * 4096, 700_000))
+            w = np.exp(rng.normal(size=n) * rng.uniform(0.1, 15.0))
+            w /= w.sum()
+            a, b = multi.cumsum(w), single.cumsum(w)
+            assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), (k, n)
+    finally:
+        multi.close()
+        single.close()

@@ -65,6 +65,8 @@ struct hmx_ctx {
     DevBuf theta, cond_id, pairs, status, iters, trips, logL, obs_state, traj, sig2, x1;
     DevBuf st_in0, st_in1, st_in2, st_out0, st_out1, partial, cs, order, logL_scratch;
     DevBuf g_traj, g_pull, g_grad, g_dstate;  // hmx_loglik_grad_batch
+    DevBuf cs_info;                            // multi-CTA cumulative sum: per-tile records
+    bool cumsum_single_cta = false;            // HMX_CUMSUM_SINGLE_CTA=1: the single-CTA kernel for every N (tests compare the two)
     DevBuf m_props, m_theta, m_cond, m_inside, m_ll, m_status, m_in_theta, m_in_logL, m_out_theta, m_out_logL, m_groups;  // hmx_mutate
     unsigned long long* d_mut_counts = nullptr;  // [8] accepted, candidates, nonfinite, maxiter, singular
     SchedState* d_sched = nullptr;
@@ -523,6 +525,7 @@ int hmx_create(hmx_ctx** out, const hmx_config* cfg, int32_t device) {
     // guarantees "merged launches == separate launches" and "sharded == single GPU" (both bitwise) would go.
     ctx->coop_max_evals = 0;
     if (const char* cm = getenv("HMX_COOP_MAX_EVALS")) ctx->coop_max_evals = atoll(cm);
+    if (const char* sc = getenv("HMX_CUMSUM_SINGLE_CTA")) ctx->cumsum_single_cta = atoi(sc) != 0;
     if (const char* fr = getenv("HMX_FORCE_REFERENCE_LOOP")) ctx->force_reference_loop = atoi(fr) != 0;
     if (const char* ce = getenv("HMX_CHUNK_EVALS")) {
         const long long v = atoll(ce);
@@ -540,7 +543,7 @@ void hmx_destroy(hmx_ctx* ctx) {
                       &ctx->obs_state, &ctx->traj, &ctx->sig2, &ctx->x1, &ctx->st_in0, &ctx->st_in1, &ctx->st_in2, &ctx->st_out0, &ctx->st_out1,
                       &ctx->partial, &ctx->cs, &ctx->order, &ctx->m_props, &ctx->m_theta, &ctx->m_cond, &ctx->m_inside,
                       &ctx->m_ll, &ctx->m_status, &ctx->m_in_theta, &ctx->m_in_logL, &ctx->m_out_theta, &ctx->m_out_logL, &ctx->row_map, &ctx->m_groups, &ctx->logL_scratch,
-                      &ctx->g_traj, &ctx->g_pull, &ctx->g_grad, &ctx->g_dstate};
+                      &ctx->g_traj, &ctx->g_pull, &ctx->g_grad, &ctx->g_dstate, &ctx->cs_info};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     for (void* p : ctx->populations) cudaFree(p);
@@ -915,6 +918,29 @@ int hmx_weights(hmx_ctx* ctx, const double* logL, int64_t N, double delta_beta, 
     return HMX_OK;
 }
 
+// cs = np.cumsum(w) exactly, on the whole GPU (hmx_stage.cuh, K4a multi-CTA); the single-CTA kernel serves small N
+static int cumsum_impl(hmx_ctx* ctx, const double* d_w, long long N, double* d_cs) {
+    const long long n_tiles = (N + kCumsumTile - 1) / kCumsumTile;
+    if (n_tiles < 4 || ctx->cumsum_single_cta) {
+        cumsum_serial_kernel<<<1, kRedThreads, 0, ctx->stream>>>(d_w, N, d_cs);
+        CU(cudaGetLastError());
+        ++ctx->launches;
+        return 0;
+    }
+    int rc;
+    if ((rc = ensure(ctx, ctx->cs_info, (size_t)n_tiles * (sizeof(CumsumTileInfo) + sizeof(double))))) return rc;
+    CumsumTileInfo* info = (CumsumTileInfo*)ctx->cs_info.p;
+    double* tile_sum = (double*)((char*)ctx->cs_info.p + (size_t)n_tiles * sizeof(CumsumTileInfo));
+    cumsum_tile_sum_kernel<<<(unsigned)n_tiles, kRedThreads, 0, ctx->stream>>>(d_w, N, tile_sum);
+    cumsum_guess_kernel<<<1, kRedThreads, 0, ctx->stream>>>(tile_sum, (int)n_tiles, info);
+    cumsum_tile_round_kernel<<<(unsigned)n_tiles, kRedThreads, 0, ctx->stream>>>(d_w, N, info);
+    cumsum_carry_kernel<<<1, kRedThreads, 0, ctx->stream>>>(d_w, N, (int)n_tiles, info, d_cs);
+    cumsum_tile_write_kernel<<<(unsigned)n_tiles, kRedThreads, 0, ctx->stream>>>(d_w, N, info, d_cs);
+    CU(cudaGetLastError());
+    ctx->launches += 5;
+    return 0;
+}
+
 int hmx_cumsum(hmx_ctx* ctx, const double* w, int64_t N, double* cs) {
     if (!ctx) return HMX_ERR_INVALID;
     if (N <= 0 || !w || !cs) return fail(ctx, HMX_ERR_INVALID, "hmx_cumsum: bad arguments");
@@ -924,9 +950,7 @@ int hmx_cumsum(hmx_ctx* ctx, const double* w, int64_t N, double* cs) {
     void *d_cs, *h_cs;
     if ((rc = stage_in(ctx, w, (size_t)N * sizeof(double), ctx->st_in0, &d_w))) return rc;
     if ((rc = stage_out(ctx, cs, (size_t)N * sizeof(double), ctx->cs, &d_cs, &h_cs))) return rc;
-    cumsum_serial_kernel<<<1, kRedThreads, 0, ctx->stream>>>((const double*)d_w, N, (double*)d_cs);
-    CU(cudaGetLastError());
-    ++ctx->launches;
+    if ((rc = cumsum_impl(ctx, (const double*)d_w, N, (double*)d_cs))) return rc;
     if (h_cs) {
         CU(cudaMemcpyAsync(h_cs, d_cs, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
@@ -944,10 +968,10 @@ int hmx_resample(hmx_ctx* ctx, const double* w, int64_t N, double u, int64_t* id
     if ((rc = stage_in(ctx, w, (size_t)N * sizeof(double), ctx->st_in0, &d_w))) return rc;
     if ((rc = stage_out(ctx, idx, (size_t)N * sizeof(int64_t), ctx->st_out0, &d_idx, &h_idx))) return rc;
     if ((rc = ensure(ctx, ctx->cs, (size_t)N * sizeof(double)))) return rc;
-    cumsum_serial_kernel<<<1, kRedThreads, 0, ctx->stream>>>((const double*)d_w, N, (double*)ctx->cs.p);
+    if ((rc = cumsum_impl(ctx, (const double*)d_w, N, (double*)ctx->cs.p))) return rc;
     searchsorted_kernel<<<red_blocks(N), kRedThreads, 0, ctx->stream>>>((const double*)ctx->cs.p, N, u, (long long*)d_idx);
     CU(cudaGetLastError());
-    ctx->launches += 2;
+    ctx->launches += 1;
     if (h_idx) {
         CU(cudaMemcpyAsync(h_idx, d_idx, (size_t)N * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));

@@ -291,6 +291,171 @@ __global__ void __launch_bounds__(kRedThreads) cumsum_serial_kernel(const double
     }
 }
 
+
+// ---- K4a, multi-CTA: the same exact cumulative sum, tiles processed by the whole GPU ------------------------------------
+// The dependency between tiles is only the running sum that enters a tile.  Inside a run of consecutive tiles whose
+// running sum stays in ONE binade and that contain no tie / oversized / irregular weight, that running sum is
+// S_entry(t) = S_start + sum of the tiles' integer totals -- an INTEGER prefix sum, exact and associative.  So:
+//   A  cumsum_tile_sum_kernel      (all CTAs)  plain floating-point sum of every tile (only used to GUESS the binade)
+//   B  cumsum_guess_kernel         (1 CTA)     scan of the tile sums -> guessed exponent of the running sum entering each tile
+//   C  cumsum_tile_round_kernel    (all CTAs)  per tile, with the guessed exponent: q_i = RN(w_i / ulp), total = sum q_i, tie / irregular flag
+//   D  cumsum_carry_kernel         (1 thread)  walks the TILES in order with the exact running sum: a tile whose guess was right,
+//                                              is regular and does not cross its binade advances the running sum by one integer
+//                                              add; any other tile is walked as the literal chain of rounded adds (11 clk/element)
+//                                              and written at once.  Records the entering mantissa of every fast tile.
+//   E  cumsum_tile_write_kernel    (all CTAs)  fast tiles: integer block scan from the recorded mantissa, doubles assembled from bits
+// The guess can be wrong (a tile sum within rounding of a power of two): D detects it by comparing exponents and falls back
+// to the chain for that tile, so the result never depends on the guess -- it is the sequentially rounded np.cumsum chain
+// bit for bit, like the single-CTA kernel above (kept as the N < 2 tiles path and as the reference in the tests).
+struct CumsumTileInfo {
+    unsigned long long total;   // sum of the rounded weights in units of the guessed ulp
+    unsigned long long S_entry; // mantissa (with hidden bit) of the running sum entering the tile (written by D)
+    int e_guess;                // guessed biased exponent of the running sum entering the tile
+    int mode;                   // C: 0 regular, 1 irregular;  D: 0 fast (E writes it), 1 done by the chain
+};
+
+__global__ void __launch_bounds__(kRedThreads) cumsum_tile_sum_kernel(const double* __restrict__ w, long long N, double* __restrict__ tile_sum) {
+    __shared__ double sm[8];
+    const long long base = (long long)blockIdx.x * kCumsumTile;
+    double s = 0.0;
+    for (int t = threadIdx.x; t < kCumsumTile; t += blockDim.x)
+        if (base + t < N) s += w[base + t];
+    s = block_reduce<false>(s, sm);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(kRedThreads) cumsum_guess_kernel(const double* __restrict__ tile_sum, int n_tiles, CumsumTileInfo* info) {
+    // serial over the tiles in one thread: n_tiles = N / 4096 (512 for 2 M particles), a few microseconds
+    if (threadIdx.x == 0) {
+        double c = 0.0;
+        for (int t = 0; t < n_tiles; ++t) {
+            const unsigned long long b = (unsigned long long)__double_as_longlong(c);
+            info[t].e_guess = (int)((b >> 52) & 0x7ffull);
+            c += tile_sum[t];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kRedThreads) cumsum_tile_round_kernel(const double* __restrict__ w, long long N, CumsumTileInfo* info) {
+    __shared__ unsigned long long sm_tot[kRedThreads / 32];
+    const long long base = (long long)blockIdx.x * kCumsumTile;
+    const int e = info[blockIdx.x].e_guess;
+    bool bad = (e == 0 || e == 0x7ff);
+    unsigned long long run = 0ull;
+    const int t0 = threadIdx.x * kCumsumPerThread;
+#pragma unroll
+    for (int j = 0; j < kCumsumPerThread; ++j) {
+        const long long i = base + t0 + j;
+        const double x = (i < N) ? w[i] : 0.0;
+        run += cumsum_round_weight(x, e > 0 ? e : 1, bad);
+    }
+    for (int o = 16; o > 0; o >>= 1) run += __shfl_down_sync(0xffffffffu, run, o);
+    if ((threadIdx.x & 31) == 0) sm_tot[threadIdx.x >> 5] = run;
+    const int any_bad = __syncthreads_or(bad ? 1 : 0);
+    if (threadIdx.x == 0) {
+        unsigned long long tot = 0ull;
+        for (int k = 0; k < kRedThreads / 32; ++k) tot += sm_tot[k];
+        info[blockIdx.x].total = tot;
+        info[blockIdx.x].mode = (any_bad || tot >= (1ull << 53)) ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(kRedThreads) cumsum_carry_kernel(const double* __restrict__ w, long long N, int n_tiles, CumsumTileInfo* info,
+                                                                   double* __restrict__ cs) {
+    __shared__ double tile[kCumsumTile];
+    __shared__ double carry_sh;
+    __shared__ int chain_sh;
+    if (threadIdx.x == 0) carry_sh = 0.0;
+    __syncthreads();
+    for (int t = 0; t < n_tiles; ++t) {
+        if (threadIdx.x == 0) {
+            const double c = carry_sh;
+            const unsigned long long cb = (unsigned long long)__double_as_longlong(c);
+            const int e = (int)((cb >> 52) & 0x7ffull);
+            const unsigned long long S = (cb & ((1ull << 52) - 1)) | (1ull << 52);
+            const bool regular = !(cb >> 63) && e != 0 && e != 0x7ff && e == info[t].e_guess && info[t].mode == 0;
+            if (regular && S + info[t].total < (1ull << 53)) {
+                info[t].S_entry = S;
+                const unsigned long long tot = S + info[t].total;
+                carry_sh = __longlong_as_double((long long)(((unsigned long long)e << 52) | (tot & ((1ull << 52) - 1))));
+                chain_sh = 0;
+            } else {
+                info[t].mode = 1;  // guess wrong, irregular weights or a binade crossing inside the tile
+                chain_sh = 1;
+            }
+        }
+        __syncthreads();
+        if (chain_sh) {  // the literal chain of rounded adds, operands staged in shared memory (11 clk per element)
+            const long long base = (long long)t * kCumsumTile;
+            const int n = (int)((N - base < kCumsumTile) ? (N - base) : kCumsumTile);
+            for (int k = threadIdx.x; k < n; k += blockDim.x) tile[k] = w[base + k];
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double c = carry_sh;
+                int k = 0;
+                for (; k + 8 <= n; k += 8) {
+                    const double x0 = tile[k], x1 = tile[k + 1], x2 = tile[k + 2], x3 = tile[k + 3];
+                    const double x4 = tile[k + 4], x5 = tile[k + 5], x6 = tile[k + 6], x7 = tile[k + 7];
+                    c = __dadd_rn(c, x0); tile[k] = c;
+                    c = __dadd_rn(c, x1); tile[k + 1] = c;
+                    c = __dadd_rn(c, x2); tile[k + 2] = c;
+                    c = __dadd_rn(c, x3); tile[k + 3] = c;
+                    c = __dadd_rn(c, x4); tile[k + 4] = c;
+                    c = __dadd_rn(c, x5); tile[k + 5] = c;
+                    c = __dadd_rn(c, x6); tile[k + 6] = c;
+                    c = __dadd_rn(c, x7); tile[k + 7] = c;
+                }
+                for (; k < n; ++k) {
+                    c = __dadd_rn(c, tile[k]);
+                    tile[k] = c;
+                }
+                carry_sh = c;
+            }
+            __syncthreads();
+            for (int k = threadIdx.x; k < n; k += blockDim.x) cs[base + k] = tile[k];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) cs[N - 1] = 1.0;  // TM:196 (the write kernel skips this element)
+}
+
+__global__ void __launch_bounds__(kRedThreads) cumsum_tile_write_kernel(const double* __restrict__ w, long long N, const CumsumTileInfo* info,
+                                                                        double* __restrict__ cs) {
+    __shared__ unsigned long long warp_tot[kRedThreads / 32];
+    const CumsumTileInfo ti = info[blockIdx.x];
+    if (ti.mode != 0) return;  // written by the chain
+    const long long base = (long long)blockIdx.x * kCumsumTile;
+    const int e = ti.e_guess;
+    bool bad = false;
+    unsigned long long pre[kCumsumPerThread];
+    unsigned long long run = 0ull;
+    const int t0 = threadIdx.x * kCumsumPerThread;
+#pragma unroll
+    for (int j = 0; j < kCumsumPerThread; ++j) {
+        const long long i = base + t0 + j;
+        run += cumsum_round_weight((i < N) ? w[i] : 0.0, e, bad);
+        pre[j] = run;
+    }
+    unsigned long long incl = run;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += v;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    unsigned long long offset = incl - run;
+    for (int k = 0; k < (int)(threadIdx.x >> 5); ++k) offset += warp_tot[k];
+    const unsigned long long ebits = (unsigned long long)e << 52;
+#pragma unroll
+    for (int j = 0; j < kCumsumPerThread; ++j) {
+        const long long i = base + t0 + j;
+        if (i < N - 1) {  // element N - 1 is forced to 1.0 by the carry kernel
+            const unsigned long long tot = ti.S_entry + offset + pre[j];
+            cs[i] = __longlong_as_double((long long)(ebits | (tot & ((1ull << 52) - 1))));
+        }
+    }
+}
+
 // K4b: idx_i = clip(searchsorted(cs, (u+i)/N, side='left'), 0, N-1)   (TM:194,198)
 __global__ void __launch_bounds__(kRedThreads) searchsorted_kernel(const double* __restrict__ cs, long long N, double u,
                                                                     long long* __restrict__ idx) {

@@ -86,15 +86,14 @@ def _usable(phi: np.ndarray) -> np.ndarray:
 def generate_dataset(n_samples: int, bounds, seed: int = 42, maxtimestep: int = 500, dt: float = 1e-5, n_time_out: int = 100,
                      theta_map: Optional[np.ndarray] = None, map_frac: float = 0.3, map_std_frac: float = 0.1, expand_bounds: bool = True,
                      posterior_samples: Optional[np.ndarray] = None, posterior_frac: float = 0.5, device: int = 0, solver=None,
-                     jit_warmup_draw: bool = True) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+                     jit_warmup_draw: bool = True, block: int = 2048) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
     """(theta[N,20], phi[N,n_time_out,5], t_out, bounds) -- the surrogate training set of the reference
     (deeponet/generate_training_data.py:144-333), same random stream and same category order (posterior draws first,
     then MAP-centred, then uniform; a failed solve is redrawn in place), but the solves run as GPU batches.
 
-    Differences from the reference, none of which change the returned arrays: the usability test of a trajectory looks
-    at the full T+1 levels in the reference and at the n_time_out stored levels here (a non-finite state anywhere still
-    rejects: the status word covers every level); `jit_warmup_draw` keeps the reference's one discarded draw
-    ("Warming up JIT", :249-251) so that the stream lines up."""
+    The usability test of a trajectory (finite, phi within [-0.5, 1.5]) looks at all T+1 levels like the reference's;
+    candidates are solved in blocks of `block` and a failure discards at most the rest of its block; `jit_warmup_draw` keeps
+    the reference's one discarded draw ("Warming up JIT", :249-251) so that the stream lines up."""
     bounds = np.array(bounds, dtype=np.float64, copy=True)
     if expand_bounds:
         bounds = expand_bounds_to_include(bounds, theta_map)
@@ -140,11 +139,20 @@ def generate_dataset(n_samples: int, bounds, seed: int = 42, maxtimestep: int = 
             cand.append(th)
             kinds.append(0 if use_post else (1 if use_map else 2))
         cand = np.array(cand)
-        g, st = solver.run_deterministic_batch(cand, rows=rows, return_status=True)
-        phi = g[:, :, :5]
-        good = _usable(phi) & ((st & 1) == 0)
-        bad = np.nonzero(~good)[0]
-        upto = int(bad[0]) if bad.size else len(cand)
+        # Solve block by block and stop at the first unusable trajectory: a failure costs at most one block of solves.  The
+        # usability test scans ALL maxtimestep + 1 levels like the reference (generate_training_data.py:266-272), so the whole
+        # trajectory of a block comes back (48 KB per solve at 500 steps) and is down-sampled here.
+        phi_blocks, upto = [], len(cand)
+        for lo in range(0, len(cand), block):
+            g, st = solver.run_deterministic_batch(cand[lo:lo + block], return_status=True)
+            good = _usable(g[:, :, :5]) & ((st & 1) == 0)
+            phi_blocks.append(g[:, rows, :5])
+            bad = np.nonzero(~good)[0]
+            if bad.size:
+                upto = lo + int(bad[0])
+                break
+        phi = np.concatenate(phi_blocks, axis=0)
+        bad = np.array([upto]) if upto < len(cand) else np.array([], dtype=int)
         for k in range(upto):
             thetas.append(cand[k])
             phis.append(phi[k])

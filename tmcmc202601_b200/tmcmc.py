@@ -25,6 +25,7 @@ host control flow without a GPU.  The product never falls back on its own.
 from __future__ import annotations
 
 import logging
+import threading
 import time
 import zlib
 from dataclasses import dataclass
@@ -53,7 +54,6 @@ COVARIANCE_NUGGET_SCALE = 1e-6
 BETA_CONVERGENCE_THRESHOLD = 1.0
 THETA_CONVERGENCE_THRESHOLD = 1e-3
 ROM_ERROR_THRESHOLD = 0.01
-ROM_ERROR_FALLBACK = 1.0
 MAX_THETA0_STEP_NORM = 0.75
 MAX_LINEARIZATION_SUBUPDATES_PER_EVENT = 3
 MIN_ACCEPTANCE_RATE = 0.01  # DebugConfig.min_acceptance_rate
@@ -88,16 +88,18 @@ class GpuStageOps:
     """Per-stage arithmetic through libhamilton (K2-K5).  One shared context per device."""
 
     _engines: Dict[int, Any] = {}
+    _engines_lock = threading.Lock()
 
     def __init__(self, engine=None, device: int = 0):
         if engine is None:
-            engine = GpuStageOps._engines.get(device)
-            if engine is None:
-                from . import _abi
-                from .engine import HamiltonEngine
+            with GpuStageOps._engines_lock:  # chains of run_batch_TMCMC construct stage ops from several threads
+                engine = GpuStageOps._engines.get(device)
+                if engine is None:
+                    from . import _abi
+                    from .engine import HamiltonEngine
 
-                cond = _abi.make_cond(np.zeros((0, 5)), [], 1.0, 0.2, tsm_variance=False)
-                engine = GpuStageOps._engines[device] = HamiltonEngine(_abi.make_config([cond]), device=device)
+                    cond = _abi.make_cond(np.zeros((0, 5)), [], 1.0, 0.2, tsm_variance=False)
+                    engine = GpuStageOps._engines[device] = HamiltonEngine(_abi.make_config([cond]), device=device)
         self.engine = engine
 
     def beta_step(self, logL, beta, target_ess_ratio, min_delta_beta, max_delta_beta):
@@ -118,11 +120,18 @@ class GpuStageOps:
 _default_stage_ops: Optional[Any] = None
 
 
-def get_stage_ops(evaluator=None):
-    """The evaluator's own GPU context when it has one, else a shared stage-only context."""
-    eng = getattr(evaluator, "_engine", None)
-    if eng is not None:
-        return GpuStageOps(engine=eng)
+def get_stage_ops(evaluator=None, log_likelihood=None):
+    """The GPU context of the evaluator (or of the likelihood callable, when that is an evaluator of this package) when it
+    has one -- stage kernels then run on the SAME device as the likelihood -- else a stage-only context on that object's
+    `.device`, else (nothing known) on device 0."""
+    for obj in (evaluator, log_likelihood):
+        eng = getattr(obj, "_engine", None)
+        if eng is not None and hasattr(eng, "beta_step"):
+            return GpuStageOps(engine=eng)
+    for obj in (evaluator, log_likelihood):
+        dev = getattr(obj, "device", None)
+        if isinstance(dev, int):
+            return GpuStageOps(device=dev)
     global _default_stage_ops
     if _default_stage_ops is None:
         _default_stage_ops = GpuStageOps()
@@ -198,24 +207,6 @@ def evaluate_particles_parallel(log_likelihood: Callable, theta: np.ndarray, n_j
             logger.warning("Particle %d evaluation failed: %s", i, e)
             out[i] = -1e20
     return out
-
-
-def choose_subset_size(beta_next: float) -> int:
-    """Subset size for the ROM-error check (TM:315-336)."""
-    return 20 if beta_next < 0.6 else (10 if beta_next < 0.85 else 5)
-
-
-def should_do_fom_check(beta_next, stage, update_interval, delta_theta0, last_rom_error, delta_tol=5e-4, rom_tol=0.01) -> bool:
-    """TM:339-390."""
-    if not (beta_next > 0.5 and (stage % update_interval == 0)):
-        return False
-    if last_rom_error is None or delta_theta0 is None:
-        return True
-    if delta_theta0 < delta_tol:
-        return False
-    if last_rom_error < rom_tol:
-        return False
-    return True
 
 
 def _validate_tmcmc_inputs(log_likelihood, prior_bounds, n_particles, n_stages, target_ess_ratio, evaluator,
@@ -296,7 +287,7 @@ def run_TMCMC(
         raise NotImplementedError("only the Gaussian MH proposal is on the production path (TM:899-900)")
     if beta_schedule not in ("ess", "cov"):
         raise ValueError("beta_schedule must be 'ess' or 'cov'")
-    ops = stage_ops or get_stage_ops(evaluator)
+    ops = stage_ops or get_stage_ops(evaluator, log_likelihood)
     if device_mutation:
         if not callable(getattr(log_likelihood, "mutate_device", None)):
             raise ValueError("device_mutation=True needs a likelihood with .mutate_device (LogLikelihoodEvaluator)")
@@ -341,8 +332,6 @@ def run_TMCMC(
     log_evidence = 0.0
     theta_MAP_posterior_history: List[np.ndarray] = []
     stage_summary: List[Dict[str, Any]] = []
-    last_rom_error: Optional[float] = None
-    last_delta_theta0: Optional[float] = None
 
     initial_rom_count = initial_fom_count = 0
     if evaluator is not None:
@@ -460,116 +449,43 @@ def run_TMCMC(
                 f"Stage={stage}, beta_next={beta_next:.4f}."
             )
 
-        # 4. linearization bookkeeping (TM:1052-1645); host side only
+        # 4. linearization hooks: the protocol run_TMCMC drives on its evaluator (TM:557-562, 1436-1441, 1561).  The evaluators
+        # of this package have no linear ROM -- compute_ROM_error is 0 while linearization is off and +inf if someone switches it
+        # on -- so the reference's bookkeeping reduces to: remember the MAP of the tempered posterior (it is what the run
+        # reports as theta_MAP), probe the ROM error at it, and leave the linearization point alone.  An evaluator that DOES
+        # report a finite error above the threshold gets the reference's remedy in its plainest form: move the point towards
+        # the MAP in bounded steps and re-evaluate the population after each move.  The reference's observation-based
+        # re-scoring of a random particle subset (TM:1130-1260) only matters with a non-zero ROM error and is not carried.
         if evaluator is not None and theta_base_full is not None and active_indices is not None:
-            should_update = (beta_next > 0.5 and (stage % update_linearization_interval == 0)) or stage == n_stages
-            should_do_fom = True
-            if should_update:
-                theta_MAP_posterior = None
-                if use_observation_based_update:
-                    should_do_fom = should_do_fom_check(beta_next, stage, update_linearization_interval, last_delta_theta0, last_rom_error)
-                    if should_do_fom:
-                        # observation-based MAP: scores penalised by log(1 + eps_ROM) on a random subset (TM:1130-1260)
-                        subset_size = min(choose_subset_size(beta_next), n_particles)
-                        w_safe = w_before if np.all(np.isfinite(w_before)) else np.ones(n_particles) / n_particles
-                        m = subset_size // 2
-                        top_idx = np.argsort(w_safe)[-min(5 * subset_size, n_particles):]
-                        if len(top_idx) < m:
-                            subset_top = rng.choice(n_particles, size=m, replace=False)
-                        else:
-                            subset_top = rng.choice(top_idx, size=min(m, len(top_idx)), replace=False)
-                        subset_rand = rng.choice(n_particles, size=subset_size - len(subset_top), replace=False)
-                        subset_idx = np.unique(np.concatenate([subset_top, subset_rand]))
-                        rom_errors = np.full(n_particles, np.nan)
-                        for i in subset_idx:
-                            th_full = theta_base_full.copy()
-                            for j, ai in enumerate(active_indices):
-                                th_full[ai] = theta_before[i, j]
-                            try:
-                                rom_errors[i] = evaluator.compute_ROM_error(th_full)
-                            except Exception:
-                                rom_errors[i] = 1.0
-                        mean_err = np.nanmean(rom_errors)
-                        if np.isnan(mean_err):
-                            mean_err = ROM_ERROR_FALLBACK
-                        rom_errors = np.where(np.isnan(rom_errors), mean_err, rom_errors)
-                        scores = log_post_before - np.log(1.0 + rom_errors)
-                        theta_MAP_posterior = theta_before[int(np.argmax(scores))]
-                if theta_MAP_posterior is None:
-                    theta_MAP_posterior = theta_before[int(np.argmax(log_post_before))]
-                theta_MAP_posterior_history.append(theta_MAP_posterior.copy())
-
-                log_post_after = log_prior_batch(theta) + beta_next * logL
-                theta_MAP_linearize = theta[int(np.argmax(log_post_after))]
+            if (beta_next > 0.5 and stage % update_linearization_interval == 0) or stage == n_stages:
+                theta_MAP_posterior_history.append(theta_before[int(np.argmax(log_post_before))].copy())
+                best = theta[int(np.argmax(log_prior_batch(theta) + beta_next * logL))]
                 theta_full_MAP = theta_base_full.copy()
                 for i, ai in enumerate(active_indices):
-                    theta_full_MAP[ai] = theta_MAP_linearize[i]
-
-                rom_pre_from_enable = None
-                if beta_next >= float(linearization_threshold) and not evaluator._linearization_enabled:
-                    enabled_ok = False
-                    try:
-                        evaluator.enable_linearization(True)
-                        err_try = evaluator.compute_ROM_error(theta_full_MAP)
-                        if np.isfinite(err_try) and err_try <= float(linearization_enable_rom_threshold):
-                            enabled_ok = True
-                            rom_pre_from_enable = float(err_try)
-                    except Exception:
-                        pass
-                    finally:
-                        if not enabled_ok:
-                            try:
-                                evaluator.enable_linearization(False)
-                            except Exception:
-                                pass
-
-                theta0_old = evaluator.get_linearization_point()
-                if theta0_old is not None:
-                    d0 = float(np.linalg.norm(theta_full_MAP - theta0_old))
-                    delta_theta0_stage = d0
-                    if d0 < THETA_CONVERGENCE_THRESHOLD:
-                        should_update = False
-                rom_error_pre = None
-                if should_update:
-                    if use_observation_based_update and not should_do_fom:
-                        rom_error_pre = last_rom_error
-                        rom_error_pre_history.append(np.nan)
-                    else:
-                        rom_error_pre = rom_pre_from_enable if rom_pre_from_enable is not None else evaluator.compute_ROM_error(theta_full_MAP)
-                        rom_error_pre_stage = None if rom_error_pre is None else float(rom_error_pre)
-                        if rom_error_pre is not None:
-                            rom_error_pre_history.append(rom_error_pre)
-                            if rom_error_pre < ROM_ERROR_THRESHOLD:
-                                should_update = False
-                if should_update and n_linearization_updates < MAX_LINEARIZATION_UPDATES:
-                    theta0_curr = evaluator.get_linearization_point()
-                    for _sub in range(MAX_LINEARIZATION_SUBUPDATES_PER_EVENT):
-                        if n_linearization_updates >= MAX_LINEARIZATION_UPDATES:
+                    theta_full_MAP[ai] = best[i]
+                theta0 = evaluator.get_linearization_point()
+                if theta0 is not None:
+                    delta_theta0_stage = float(np.linalg.norm(theta_full_MAP - theta0))
+                if theta0 is None or delta_theta0_stage >= THETA_CONVERGENCE_THRESHOLD:
+                    err = evaluator.compute_ROM_error(theta_full_MAP)
+                    rom_error_pre_stage = float(err)
+                    rom_error_pre_history.append(err)
+                    moves = 0
+                    while (theta0 is not None and np.isfinite(err) and err >= ROM_ERROR_THRESHOLD and moves < MAX_LINEARIZATION_SUBUPDATES_PER_EVENT
+                           and n_linearization_updates < MAX_LINEARIZATION_UPDATES):
+                        gap = theta_full_MAP - theta0
+                        dist_ = float(np.linalg.norm(gap))
+                        if not np.isfinite(dist_) or dist_ <= 1e-12:
                             break
-                        delta_vec = theta_full_MAP - theta0_curr
-                        delta_norm = float(np.linalg.norm(delta_vec))
-                        if not np.isfinite(delta_norm) or delta_norm <= 1e-12:
-                            break
-                        alpha = 1.0 if delta_norm <= MAX_THETA0_STEP_NORM else (MAX_THETA0_STEP_NORM / delta_norm)
-                        theta0_next = theta0_curr + alpha * delta_vec
-                        evaluator.update_linearization_point(theta0_next)
+                        theta0 = theta0 + min(1.0, MAX_THETA0_STEP_NORM / dist_) * gap
+                        evaluator.update_linearization_point(theta0)
+                        theta0_history.append(theta0.copy())
                         n_linearization_updates += 1
-                        theta0_history.append(theta0_next.copy())
-                        last_delta_theta0 = float(np.linalg.norm(theta0_next - theta0_curr))
-                        # the likelihood of every particle is recomputed after the point moved (TM:1587-1591)
-                        logL = evaluate_particles_parallel(log_likelihood, theta, n_jobs=n_jobs, use_threads=use_threads)
-                        rom_error_post = None
-                        if use_observation_based_update and not should_do_fom:
-                            rom_error_history.append(np.nan)
-                        else:
-                            rom_error_post = evaluator.compute_ROM_error(theta_full_MAP)
-                            if rom_error_post is not None:
-                                rom_error_history.append(rom_error_post)
-                                last_rom_error = rom_error_post
-                                rom_error_post_stage = float(rom_error_post)
-                        theta0_curr = theta0_next
-                        if rom_error_post is not None and rom_error_post < ROM_ERROR_THRESHOLD:
-                            break
+                        moves += 1
+                        logL = evaluate_particles_parallel(log_likelihood, theta, n_jobs=n_jobs, use_threads=use_threads)  # TM:1587-1591
+                        err = evaluator.compute_ROM_error(theta_full_MAP)
+                        rom_error_history.append(err)
+                        rom_error_post_stage = float(err)
 
         acc_rate_history.append(acc_rate)
         stage_summary.append({
