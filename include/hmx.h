@@ -242,6 +242,29 @@ int hmx_weighted_scatter(hmx_ctx* ctx, const double* theta, const double* w, int
 int hmx_log_likelihood_sparse(hmx_ctx* ctx, const double* mu, const double* sig, const double* data,
                               const double* sigma_obs, const double* weights, int32_t n_obs, double* logL);
 
+/* ---- several GPUs of one box behind one handle -------------------------------------------------
+ * For HOST callers (the reference is a single NumPy process): one context per listed device, the flat evaluation list
+ * split into contiguous blocks of ceil(N / n_devices), every block copied, solved and copied back by its own device
+ * concurrently (one host thread per device).  The log-likelihoods land in the caller's array in input order -- the
+ * "all-gather" -- so the replicated stage arithmetic (hmx_beta_step / hmx_weights / hmx_resample on
+ * hmx_multi_context(m, 0)) sees the whole population; hmx_multi_weighted_cov is the "all-reduce": shard-local moments and
+ * scatter summed in device order.  Evaluations are independent, so there is no device-to-device traffic on this path.
+ * Device-RESIDENT multi-GPU callers use one process and one hmx_ctx per GPU and exchange log-likelihoods / covariance
+ * partials with NCCL (tmcmc202601_b200/distributed.py, `torchrun`; INTEGRATION.md shows the recipe).
+ * Likelihood values do not depend on the number of devices (bitwise); the covariance agrees to rounding (the partial
+ * sums associate by shard). */
+typedef struct hmx_multi hmx_multi;
+int hmx_multi_create(hmx_multi** m, const hmx_config* cfg, const int32_t* device_ids, int32_t n_devices);
+void hmx_multi_destroy(hmx_multi* m);
+const char* hmx_multi_last_error(const hmx_multi* m);
+int32_t hmx_multi_device_count(const hmx_multi* m);
+hmx_ctx* hmx_multi_context(hmx_multi* m, int32_t k);
+/* hmx_loglik_batch over all devices; theta / cond_id / logL / status / newton_iters are HOST arrays */
+int hmx_multi_loglik_batch(hmx_multi* m, const double* theta, const int32_t* cond_id, int64_t N, double* logL, uint32_t* status,
+                           uint32_t* newton_iters);
+/* hmx_weighted_cov with the particles sharded over the devices (host arrays) */
+int hmx_multi_weighted_cov(hmx_multi* m, const double* theta, const double* w, int64_t N, int32_t d, double* mean, double* cov);
+
 /* ---- measurement support ------------------------------------------------------------------------- */
 typedef struct {
     int64_t evals;         /* evaluations processed by the last hmx_loglik_batch / hmx_trajectory_batch */

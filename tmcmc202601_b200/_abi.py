@@ -182,6 +182,8 @@ EXPORTS = [
     "hmx_measure_fp64_peak",
     "hmx_mutate", "hmx_mutate_groups", "hmx_trajectory_rows", "hmx_set_latency_kernel", "hmx_cumsum",
     "hmx_tsm_obs_rows", "hmx_legacy_trajectory_rows", "hmx_loglik_grad_batch", "hmx_solve_tsm_batch", "hmx_set_sig2_guard",
+    "hmx_multi_create", "hmx_multi_destroy", "hmx_multi_last_error", "hmx_multi_device_count", "hmx_multi_context",
+    "hmx_multi_loglik_batch", "hmx_multi_weighted_cov",
     "hmx_population_create", "hmx_population_destroy", "hmx_population_upload", "hmx_population_download",
 ]
 
@@ -319,6 +321,16 @@ def load() -> C.CDLL:
     lib.hmx_population_upload.argtypes = [vp, vp, vp, C.c_int64]
     lib.hmx_population_download.argtypes = [vp, vp, vp, C.c_int64]
     lib.hmx_legacy_trajectory_rows.argtypes = [vp, C.POINTER(HmxLegacyConfig), vp, C.c_int64, vp, C.c_int32, vp, vp, vp]
+    lib.hmx_multi_create.argtypes = [C.POINTER(vp), C.POINTER(HmxConfig), vp, C.c_int32]
+    lib.hmx_multi_destroy.argtypes = [vp]
+    lib.hmx_multi_destroy.restype = None
+    lib.hmx_multi_last_error.argtypes = [vp]
+    lib.hmx_multi_last_error.restype = C.c_char_p
+    lib.hmx_multi_device_count.argtypes = [vp]
+    lib.hmx_multi_context.argtypes = [vp, C.c_int32]
+    lib.hmx_multi_context.restype = vp
+    lib.hmx_multi_loglik_batch.argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp]
+    lib.hmx_multi_weighted_cov.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp, vp]
     lib.hmx_solve_tsm_batch.argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp]
     lib.hmx_set_sig2_guard.argtypes = [vp, C.c_int32]
     lib.hmx_loglik_grad_batch.argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp, vp]

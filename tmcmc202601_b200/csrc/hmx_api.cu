@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/hmx.h"
@@ -450,6 +451,40 @@ int batch_impl(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, long l
 }
 
 }  // namespace
+
+struct hmx_multi {
+    std::vector<hmx_ctx*> ctx;
+    std::string err;
+};
+
+static thread_local std::string g_multi_create_error;
+
+// contiguous block of rank k of G over N items (the partition of SURVEY 8(e); identical to distributed.shard_bounds)
+static void multi_bounds(long long N, int G, int k, long long* lo, long long* hi) {
+    const long long per = (N + G - 1) / G;
+    *lo = std::min(N, per * k);
+    *hi = std::min(N, per * (k + 1));
+}
+
+// run fn(k, lo, hi) for every device on its own host thread; first error wins
+template <class F>
+static int multi_run(hmx_multi* m, long long N, F&& fn) {
+    const int G = (int)m->ctx.size();
+    std::vector<int> rc(G, HMX_OK);
+    std::vector<std::thread> th;
+    for (int k = 0; k < G; ++k) {
+        long long lo, hi;
+        multi_bounds(N, G, k, &lo, &hi);
+        th.emplace_back([&, k, lo, hi] { rc[k] = (hi > lo) ? fn(k, lo, hi) : HMX_OK; });
+    }
+    for (auto& t : th) t.join();
+    for (int k = 0; k < G; ++k)
+        if (rc[k] != HMX_OK) {
+            m->err = std::string("device slot ") + std::to_string(k) + ": " + hmx_last_error(m->ctx[k]);
+            return rc[k];
+        }
+    return HMX_OK;
+}
 
 extern "C" {
 
@@ -1204,6 +1239,90 @@ int hmx_mutate(hmx_ctx* ctx, const hmx_mutation* mut, const double* theta_res, c
     if (!mut || N < 0) return fail(ctx, HMX_ERR_INVALID, "hmx_mutate: NULL argument or N < 0");
     const int64_t n = N;
     return hmx_mutate_groups(ctx, 1, mut, &n, theta_res, logL_res, theta_out, logL_out, props, logL_props, stats);
+}
+
+// ---- several GPUs behind ONE handle ------------------------------------------------------------------
+int hmx_multi_create(hmx_multi** out, const hmx_config* cfg, const int32_t* device_ids, int32_t n_devices) {
+    if (!out) return HMX_ERR_INVALID;
+    *out = nullptr;
+    if (!cfg || !device_ids || n_devices < 1 || n_devices > 64) {
+        g_multi_create_error = "hmx_multi_create: need cfg, device_ids and 1 <= n_devices <= 64";
+        return HMX_ERR_INVALID;
+    }
+    hmx_multi* m = new (std::nothrow) hmx_multi();
+    if (!m) return HMX_ERR_OOM;
+    for (int k = 0; k < n_devices; ++k) {
+        hmx_ctx* c = nullptr;
+        const int rc = hmx_create(&c, cfg, device_ids[k]);
+        if (rc != HMX_OK) {
+            g_multi_create_error = std::string("device ") + std::to_string(device_ids[k]) + ": " + hmx_last_error(nullptr);
+            for (hmx_ctx* q : m->ctx) hmx_destroy(q);
+            delete m;
+            return rc;
+        }
+        m->ctx.push_back(c);
+    }
+    *out = m;
+    return HMX_OK;
+}
+
+void hmx_multi_destroy(hmx_multi* m) {
+    if (!m) return;
+    for (hmx_ctx* c : m->ctx) hmx_destroy(c);
+    delete m;
+}
+
+const char* hmx_multi_last_error(const hmx_multi* m) { return m ? m->err.c_str() : g_multi_create_error.c_str(); }
+int32_t hmx_multi_device_count(const hmx_multi* m) { return m ? (int32_t)m->ctx.size() : 0; }
+hmx_ctx* hmx_multi_context(hmx_multi* m, int32_t k) { return (m && k >= 0 && k < (int32_t)m->ctx.size()) ? m->ctx[k] : nullptr; }
+
+int hmx_multi_loglik_batch(hmx_multi* m, const double* theta, const int32_t* cond_id, int64_t N, double* logL, uint32_t* status,
+                           uint32_t* newton_iters) {
+    if (!m) return HMX_ERR_INVALID;
+    if (N < 0 || (N > 0 && (!theta || !logL))) {
+        m->err = "hmx_multi_loglik_batch: NULL argument or N < 0";
+        return HMX_ERR_INVALID;
+    }
+    if (is_device_ptr(theta) || is_device_ptr(logL)) {
+        m->err = "hmx_multi_loglik_batch shards HOST arrays; device-resident callers run one context (one process) per GPU";
+        return HMX_ERR_INVALID;
+    }
+    return multi_run(m, N, [&](int k, long long lo, long long hi) {
+        return hmx_loglik_batch(m->ctx[k], theta + lo * HMX_NTHETA, cond_id ? cond_id + lo : nullptr, hi - lo, logL + lo,
+                                nullptr, status ? status + lo : nullptr, newton_iters ? newton_iters + lo : nullptr);
+    });
+}
+
+int hmx_multi_weighted_cov(hmx_multi* m, const double* theta, const double* w, int64_t N, int32_t d, double* mean, double* cov) {
+    if (!m) return HMX_ERR_INVALID;
+    if (N <= 0 || !theta || !w || !cov || d < 1 || d > 32) {
+        m->err = "hmx_multi_weighted_cov: bad arguments (1 <= d <= 32)";
+        return HMX_ERR_INVALID;
+    }
+    const int G = (int)m->ctx.size();
+    std::vector<double> mom((size_t)G * (2 + d), 0.0), sc((size_t)G * d * d, 0.0);
+    int rc = multi_run(m, N, [&](int k, long long lo, long long hi) {
+        return hmx_weighted_moments(m->ctx[k], theta + lo * d, w + lo, hi - lo, d, mom.data() + (size_t)k * (2 + d));
+    });
+    if (rc) return rc;
+    // "all-reduce" of the shard moments in device order (deterministic), then the centred scatter per shard
+    std::vector<double> tot(2 + d, 0.0), mu(d, 0.0);
+    for (int k = 0; k < G; ++k)
+        for (int j = 0; j < 2 + d; ++j) tot[j] += mom[(size_t)k * (2 + d) + j];
+    for (int j = 0; j < d; ++j) mu[j] = tot[2 + j] / tot[0];
+    rc = multi_run(m, N, [&](int k, long long lo, long long hi) {
+        return hmx_weighted_scatter(m->ctx[k], theta + lo * d, w + lo, hi - lo, d, mu.data(), sc.data() + (size_t)k * d * d);
+    });
+    if (rc) return rc;
+    const double fact = tot[0] - tot[1] / tot[0];
+    for (int e = 0; e < d * d; ++e) {
+        double s = 0.0;
+        for (int k = 0; k < G; ++k) s += sc[(size_t)k * d * d + e];
+        cov[e] = s * (1.0 / fact);
+    }
+    if (mean)
+        for (int j = 0; j < d; ++j) mean[j] = mu[j];
+    return HMX_OK;
 }
 
 int hmx_set_latency_kernel(hmx_ctx* ctx, int64_t max_evals) {

@@ -420,3 +420,68 @@ class HamiltonEngine:
         v = C.c_double(0.0)
         self._check(self._lib.hmx_measure_fp64_peak(self._ctx, C.byref(v)), "hmx_measure_fp64_peak")
         return v.value
+
+
+class MultiEngine:
+    """Several GPUs of one box behind one handle (hmx_multi_*): NumPy arrays in, NumPy arrays out; the flat evaluation
+    list is split into contiguous blocks, one per device, solved concurrently.  `stage_engine` is the context of the first
+    device as a HamiltonEngine view for the replicated stage arithmetic."""
+
+    def __init__(self, config: _abi.HmxConfig, devices):
+        self._lib = _abi.load()
+        self._m = C.c_void_p()
+        self.config = config
+        self.devices = [int(d) for d in devices]
+        ids = (C.c_int32 * len(self.devices))(*self.devices)
+        rc = self._lib.hmx_multi_create(C.byref(self._m), C.byref(config), ids, len(self.devices))
+        if rc != 0:
+            msg = self._lib.hmx_multi_last_error(None)
+            self._m = C.c_void_p()
+            raise HmxError(f"hmx_multi_create failed ({rc}): {msg.decode() if msg else ''}")
+        self.n_cond = config.n_cond
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self._lib.hmx_multi_last_error(self._m)
+            raise HmxError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    @property
+    def stage_engine(self) -> HamiltonEngine:
+        """Borrowed view on the first device's context (do not close it)."""
+        e = HamiltonEngine.__new__(HamiltonEngine)
+        e._lib, e.config, e.device = self._lib, self.config, self.devices[0]
+        e._ctx = C.c_void_p(self._lib.hmx_multi_context(self._m, 0))
+        e.n_cond, e.n_steps = self.config.n_cond, self.config.n_steps
+        e.n_obs_max = max(self.config.cond[k].n_obs for k in range(self.config.n_cond))
+        e.close = lambda: None
+        return e
+
+    def loglik_batch(self, theta, cond_id=None, return_status=False):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        N = theta.shape[0]
+        cid = None if cond_id is None else np.ascontiguousarray(cond_id, dtype=np.int32)
+        logL = np.empty(N)
+        status = np.zeros(N, dtype=np.uint32) if return_status else None
+        iters = np.zeros(N, dtype=np.uint32) if return_status else None
+        self._check(self._lib.hmx_multi_loglik_batch(self._m, _addr(theta), _addr(cid), N, _addr(logL), _addr(status), _addr(iters)),
+                    "hmx_multi_loglik_batch")
+        return (logL, status, iters) if return_status else logL
+
+    def weighted_cov(self, theta, w):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        N, d = theta.shape
+        mean, cov = np.empty(d), np.empty((d, d))
+        self._check(self._lib.hmx_multi_weighted_cov(self._m, _addr(theta), _addr(w), N, d, _addr(mean), _addr(cov)), "hmx_multi_weighted_cov")
+        return mean, cov
+
+    def close(self):
+        if self._m:
+            self._lib.hmx_multi_destroy(self._m)
+            self._m = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
