@@ -174,7 +174,10 @@ int red_blocks(long long N) {
 
 template <bool ALPHA, int HILL>
 void launch_ode(hmx_ctx* ctx, const OdeParams& P, int blocks) {
-    ode_kernel<ALPHA, HILL><<<blocks, kOdeThreads, 0, ctx->stream>>>(P);
+    // the production exponent n_hill = 4 has its own instance of the hot kernel (HILL = 4: no exponent switch per trip);
+    // the arithmetic is the same as the generic integer-exponent instance, bit for bit
+    if (HILL == 1 && ctx->K.hill_mode == 4) ode_kernel<ALPHA, 4><<<blocks, kOdeThreads, 0, ctx->stream>>>(P);
+    else ode_kernel<ALPHA, HILL><<<blocks, kOdeThreads, 0, ctx->stream>>>(P);
 }
 template <bool ALPHA, int HILL>
 void launch_resolve(hmx_ctx* ctx, const OdeParams& P, int blocks, int force) {
@@ -204,9 +207,10 @@ void launch_grad(hmx_ctx* ctx, const GradParams& P, int blocks) {
 }
 template <bool ALPHA, int HILL>
 int ode_occupancy() {
-    int nb = 0;
+    int nb = 0, nb4 = 1 << 30;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ode_kernel<ALPHA, HILL>, kOdeThreads, 0);
-    return nb;
+    if (HILL == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb4, ode_kernel<ALPHA, 4>, kOdeThreads, 0);
+    return std::min(nb, nb4);
 }
 
 #define HMX_DISPATCH(FN, ...)                                  \

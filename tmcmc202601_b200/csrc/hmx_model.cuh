@@ -64,11 +64,18 @@ HMX_HD double rcp(double x) {
 #if defined(__CUDA_ARCH__) && !defined(HMX_IEEE_DIV)
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#if defined(HMX_RCP_CUBIC)
+    // one third-order step: y (1 + e + e^2) with e = 1 - x y; the seed is good to 2^-23, so the error becomes e^3 <= 2^-69
+    const double e = fma(-x, y, 1.0);
+    const double t = fma(e, e, e);
+    return fma(y, t, y);
+#else
     double e = fma(-x, y, 1.0);
     y = fma(y, e, y);
     e = fma(-x, y, 1.0);
     y = fma(y, e, y);
     return y;
+#endif
 #else
     return 1.0 / x;
 #endif
@@ -174,6 +181,10 @@ HMX_HD void hill_powers(const SolverConsts& K, double x, double& xn, double& xn1
     if (HILL == 2) {
         xn = pow(x, K.n_hill);
         xn1 = pow(x, K.n_hill - 1.0);
+    } else if (HILL == 4) {  // n_hill == 4 at compile time (the production setting): no switch on the hot path
+        const double x2 = x * x;
+        xn = x2 * x2;
+        xn1 = x2 * x;
     } else {
         const double x2 = x * x;
         switch (K.hill_mode) {
@@ -199,6 +210,7 @@ struct Eval {
     double Q[12];
     double norm;                   // ||Q||_inf
     bool nan;                      // any(isnan(Q))
+    bool inbox;                    // every phi_i, psi_i of the point was strictly inside the clip box (nothing was clipped)
 };
 
 // Residual Q at the candidate x (S5:43-127).  gp = [phi_old(5), phi0_old, psi_old(5)].
@@ -217,6 +229,7 @@ HMX_HD void residual(const SolverConsts& K, const double (&x)[12], const GPT& gp
 #else
         inbox = inbox && (x[i] >= kClipLo) && (x[i] <= kClipHi) && (x[6 + i] >= kClipLo) && (x[6 + i] <= kClipHi);
 #endif
+    e.inbox = inbox;
     if (inbox) {
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
@@ -224,6 +237,8 @@ HMX_HD void residual(const SolverConsts& K, const double (&x)[12], const GPT& gp
             e.ps[i] = x[6 + i];
         }
     } else
+#else
+    e.inbox = false;
 #endif
     {
 #pragma unroll
@@ -239,13 +254,27 @@ HMX_HD void residual(const SolverConsts& K, const double (&x)[12], const GPT& gp
     for (int i = 0; i < 5; ++i) {
         const double v = e.ph[i], u = e.ps[i];
         const double wv = fma(v, v, -v), wu = fma(u, u, -u);
+#if defined(HMX_RCP_PAIR)
+        const double rvu = rcp(wv * wu);  // one reciprocal for the pair: 1/wv = wu / (wv wu), 1/wu = wv / (wv wu)
+        const double rv = rvu * wu, ru = rvu * wv;
+#else
         const double rv = rcp(wv), ru = rcp(wu);
+#endif
         const double sv = fma(2.0, v, -1.0), su = fma(2.0, u, -1.0);
+#if defined(HMX_FOLD_CONSTS)
+        // -2 Kp1 (2v - 1) as ONE fma, 4 Kp1 (5 w + 3) as ONE fma (the constants are folded on the host side of the bank)
+        fph[i] = fma(2.0 * m2K, v, -m2K) * (rv * rv * rv);
+        fps[i] = fma(2.0 * m2K, u, -m2K) * (ru * ru * ru);
+        e.phip[i] = -fph[i] * fma(3.0 * sv, rv, 2.0);                        // S5:185-187
+        const double ru2 = ru * ru;
+        e.psip[i] = fma(20.0 * K.Kp1, wu, 12.0 * K.Kp1) * (ru2 * ru2);        // S5:189
+#else
         fph[i] = (m2K * sv) * (rv * rv * rv);
         fps[i] = (m2K * su) * (ru * ru * ru);
         e.phip[i] = -fph[i] * fma(3.0 * sv, rv, 2.0);                        // S5:185-187
         const double ru2 = ru * ru;
         e.psip[i] = (4.0 * K.Kp1) * fma(5.0, wu, 3.0) * (ru2 * ru2);          // S5:189
+#endif
         e.p[i] = v * u;
         e.phd[i] = (v - gp[i]) * K.inv_dt;
         e.psd[i] = (u - gp[6 + i]) * K.inv_dt;
@@ -327,6 +356,40 @@ HMX_HD bool solve5x2_natural(double (&S)[5][7]) {
             for (int cc = k + 1; cc < 7; ++cc) S[r][cc] = fma(-l, S[k][cc], S[r][cc]);
         }
     }
+#pragma unroll
+    for (int k = 4; k >= 0; --k) {
+        double s0 = S[k][5], s1 = S[k][6];
+#pragma unroll
+        for (int cc = k + 1; cc < 5; ++cc) {
+            s0 = fma(-S[k][cc], S[cc][5], s0);
+            s1 = fma(-S[k][cc], S[cc][6], s1);
+        }
+        S[k][5] = s0 * rp[k];
+        S[k][6] = s1 * rp[k];
+    }
+    return ok;
+}
+
+// Division-free variant of the natural-order elimination: row_r <- S_kk row_r - S_rk row_k.  No reciprocal sits on the
+// elimination chain (the five divisions of the back substitution are independent of each other); the pivots of
+// I + diag(g) C are ~1, so the scaled rows stay O(1).  Healthy when every scaled pivot keeps at least kPivotFloor of the
+// previous one.
+HMX_HD bool solve5x2_divfree(double (&S)[5][7]) {
+    bool ok = fabs(S[0][0]) >= kPivotFloor;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double pk = S[k][k];
+#pragma unroll
+        for (int r = k + 1; r < 5; ++r) {
+            const double l = S[r][k];
+#pragma unroll
+            for (int cc = k + 1; cc < 7; ++cc) S[r][cc] = fma(pk, S[r][cc], -l * S[k][cc]);
+        }
+        ok = ok && (fabs(S[k + 1][k + 1]) >= kPivotFloor * fabs(pk));
+    }
+    double rp[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) rp[k] = rcp(S[k][k]);
 #pragma unroll
     for (int k = 4; k >= 0; --k) {
         double s0 = S[k][5], s1 = S[k][6];
@@ -528,7 +591,9 @@ HMX_HD void direction_impl(const SolverConsts& K, const Eval& e, const AT& A, co
         S[i][5] = fma(u, a0, v * a1);
         S[i][6] = fma(u, b0, v * b1);
     }
-#if defined(HMX_SOLVE_BLOCK23)
+#if defined(HMX_SOLVE_DIVFREE)
+    const bool healthy = solve5x2_divfree(S);
+#elif defined(HMX_SOLVE_BLOCK23)
     const bool healthy = solve5x2_block23(S) >= kPivotFloor;  // shorter dependency chain, a few more live values; measured 2 % slower
 #else
     const bool healthy = solve5x2_natural(S);
