@@ -53,16 +53,16 @@ N_COND = 4
 METRIC = "particle_ode_likelihood_evals_per_sec"
 UNIT = "evals/s"
 
-# Executed FP64 flops (DFMA = 2, DMUL = DADD = 1) of the ODE kernel per residual evaluation ("trip") and per
-# quasi-Newton direction solve, calibrated from the ncu capture profiles/r01f_ode_kernel_rcp_lean.json
-# (thread-level sass op counters: 1.7576e12 DFMA + 1.1418e12 DMUL + 3.481e11 DADD thread-instructions =
-# 5.005e12 flop for the kernel's own counters of 4.5913e9 residual evaluations and 3.4175e9 directions; split
-# between the two by the static SASS count of residual() : direction() = 441 : 820 flops, scale 1.037).
-# DESIGN.md "Roofline accounting" has the derivation.
-FLOPS_PER_RESIDUAL = 457.0
-FLOPS_PER_DIRECTION = 850.0
-# DRAM bytes per evaluation of the same capture (dram__bytes_read.sum + dram__bytes_write.sum) / 262144
-DRAM_BYTES_PER_EVAL_NCU = 1041  # dram__bytes_read.sum + dram__bytes_write.sum of ode_kernel per evaluation, ncu --set full (profiles/r01j_ode_kernel_rebased.json: 59.5 + 213.3 MB for 262 144 evaluations)
+# Executed FP64 flops (DFMA = 2, DMUL = DADD = 1) of the ODE kernel per residual evaluation ("trip") and per quasi-Newton
+# direction solve, calibrated on the round-2 kernel from the ncu capture profiles/r02d_ode_kernel.json: thread-level SASS
+# counters 1.5171e12 DFMA + 1.1205e12 DMUL + 3.4125e11 DADD = 4.496e12 flop for the launch's own counters of 3.9592e9
+# residual evaluations and 3.4175e9 directions; attributed per SASS instruction to its source function through the line
+# table (residual + rebase + its reciprocals 1.6945e12 flop -> 428 per residual evaluation; direction + 2x2 blocks + 5x5
+# solve + its reciprocals 2.8015e12 -> 820 per direction).  DESIGN.md "Roofline accounting" has the derivation.
+FLOPS_PER_RESIDUAL = 428.0
+FLOPS_PER_DIRECTION = 820.0
+# DRAM bytes per evaluation of the same capture: (dram__bytes_read.sum 59.1 MB + dram__bytes_write.sum 213.6 MB) / 262144
+DRAM_BYTES_PER_EVAL_NCU = 1040
 # the reference-equivalent count of SURVEY.md section 8(d): dense Q + K + dgesv per iteration, Q per extra trial
 FP64_NOMINAL_TFLOPS = 37.2  # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
 REF_FLOPS_PER_ITER = 2778.0

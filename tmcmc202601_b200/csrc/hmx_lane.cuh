@@ -153,8 +153,10 @@ HMX_HD bool rebase_residual(const SolverConsts& K, const Lane& s, const double (
             const double v = e.ph[i], u = e.ps[i];
             const double qi = e.Q[i] - fma(fma(u, u, K.etaphi_eta[i]), e.phd[i], e.p[i] * e.psd[i]);
             const double qs = e.Q[6 + i] - fma(e.p[i], e.phd[i], v * v * e.psd[i]);
+#if !defined(HMX_TD_FROM_GP)
             e.phd[i] = 0.0;
             e.psd[i] = 0.0;
+#endif
             e.Q[i] = qi;
             e.Q[6 + i] = qs;
             nb[i] = umax64(abs_bits(qi), abs_bits(qs));
@@ -168,8 +170,10 @@ HMX_HD bool rebase_residual(const SolverConsts& K, const Lane& s, const double (
             const double v = e.ph[i], u = e.ps[i];
             const double phd = (v - s.gp[i]) * K.inv_dt, psd = (u - s.gp[6 + i]) * K.inv_dt;
             const double dph = phd - e.phd[i], dps = psd - e.psd[i];
+#if !defined(HMX_TD_FROM_GP)
             e.phd[i] = phd;
             e.psd[i] = psd;
+#endif
             const double qi = e.Q[i] + fma(fma(u, u, K.etaphi_eta[i]), dph, e.p[i] * dps);
             const double qs = e.Q[6 + i] + fma(e.p[i], dph, v * v * dps);
             e.Q[i] = qi;
@@ -306,6 +310,15 @@ HMX_HD bool lane_trip(const SolverConsts& K, Lane& s, StepEnd&& step_end) {
     // once for them and once for the lanes that just started a new time step (measured: -27 % throughput).
     HMX_WARP_CONVERGE();
     if (need_dir) {
+#if defined(HMX_TD_FROM_GP)
+        // time derivatives at the point of `e` against the CURRENT previous level, recomputed here (20 FP64 instructions)
+        // instead of being carried -- and patched by the rebase -- across the accept / step-end join (20 registers)
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            e.phd[i] = (e.ph[i] - s.gp[i]) * K.inv_dt;
+            e.psd[i] = (e.ps[i] - s.gp[6 + i]) * K.inv_dt;
+        }
+#endif
         direction<ALPHA, HILL>(K, e, s.A, s.b, s.d, s.stash);
         ++s.it;
         ++s.iters;
