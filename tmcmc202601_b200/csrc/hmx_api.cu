@@ -561,7 +561,7 @@ int hmx_create(hmx_ctx** out, const hmx_config* cfg, int32_t device) {
     ctx->coop_blocks_per_sm = query_coop_occupancy(ctx);
     // K1L is OPT-IN (hmx_set_latency_kernel / HMX_COOP_MAX_EVALS): it agrees with K1 to ~1e-12, not bit for bit, so a
     // size-dependent switch would make a likelihood depend on the size of the batch it travels in -- and with it the
-    // guarantees "merged launches == separate launches" and "sharded == single GPU" (both bitwise) would go.
+    // guarantees "merged launches == separate launches" and "sharded likelihoods == single-GPU likelihoods" (both bitwise) would go.
     ctx->coop_max_evals = 0;
     if (const char* cm = getenv("HMX_COOP_MAX_EVALS")) ctx->coop_max_evals = atoll(cm);
     if (const char* sc = getenv("HMX_CUMSUM_SINGLE_CTA")) ctx->cumsum_single_cta = atoi(sc) != 0;
