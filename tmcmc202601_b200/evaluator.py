@@ -222,6 +222,34 @@ class LogLikelihoodEvaluator:
     def __call__(self, theta_sub: np.ndarray) -> float:
         return float(self.batch(np.asarray(theta_sub, dtype=np.float64)[None, :], record_history=True)[0])
 
+    def value_and_grad(self, theta_sub: np.ndarray):
+        """(logL[N], dlogL/dtheta_sub[N, n]) for theta_sub[N, n]: what the reference's NUTS / HMC engine obtains from
+        `jax.value_and_grad(log_likelihood)` (main/tmcmc_nuts_engine.py:202), here by forward sensitivities on the GPU
+        (hmx_loglik_grad_batch).  The gradient of the full 20-vector is pulled back through the theta_sub -> theta_full
+        scatter of `_full_theta` (a column that lands on several full entries collects all of them; a column that reaches
+        no ODE parameter gets 0).  Failed solves: logL = -1e20, zero gradient."""
+        theta_sub = np.atleast_2d(np.asarray(theta_sub, dtype=np.float64))
+        N, n = theta_sub.shape
+        self.call_count += N
+        self.health.n_calls += N
+        full = self._full_theta(theta_sub)
+        ode = np.ascontiguousarray(full[:, :20])
+        lin = self._theta_linearization[:20]
+        at_lin = np.all(np.abs(ode - lin[None, :]) <= (1e-8 + 1e-5 * np.abs(lin[None, :])), axis=1)
+        with timed(self.timing, "tsm.solve_tsm"):
+            logL, g_full, status = self._engine.loglik_grad_batch(ode, at_lin.astype(np.int32))
+        self.health.n_output_nonfinite += int(((status & _abi.ST_NONFINITE) != 0).sum())
+        grad = np.zeros((N, n))
+        amap = self.mutation_map(n)
+        for j, a in enumerate(amap):
+            if 0 <= a < _abi.NTHETA:
+                grad[:, j] += g_full[:, a]
+        if self.ve_prior is not None:
+            logL = logL + np.array([self.ve_prior.log_prior(t) for t in theta_sub])
+            for ve_idx, pos in self.ve_prior._sub_positions.items():
+                grad[:, pos] -= (theta_sub[:, pos] - self.ve_prior.mu[ve_idx]) / self.ve_prior.sigma[ve_idx] ** 2
+        return logL, grad
+
     def mutation_map(self, d: int) -> List[int]:
         """Position of theta_sub[j] in the full vector, exactly as _full_theta scatters it (-1: column unused)."""
         if self.strict_mapping and d == self.theta_base.size:
