@@ -6,6 +6,7 @@ Public surface (names follow the reference):
         build_likelihood_weights, ViscoelasticPrior
     tmcmc.run_TMCMC, run_multi_chain_TMCMC, TMCMCResult, systematic_resample, evaluate_particles_parallel,
         reflect_into_bounds, compute_MAP_with_uncertainty
+    nuts.tmcmc_engine (RW / HMC / NUTS TMCMC on the likelihood gradient), evaluator.LogLikelihoodEvaluator.value_and_grad
     posterior.compute_hdi, compute_credible_intervals
     engine.HamiltonEngine (direct handle on the C ABI of include/hmx.h), distributed.ShardedEvaluator / ShardedStageOps
 Nothing here imports the CPU oracle; without libhamilton.so and a B200 the compute entry points raise.
