@@ -179,7 +179,7 @@ int hmx_loglik_grad_batch(hmx_ctx* ctx, const double* theta, const int32_t* cond
  *   g [N,n_steps+1,12] row-major;  t_arr is (arange(n_steps+1) * dt) and is left to the caller. */
 int hmx_trajectory_batch(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, int64_t N,
                          double* g, uint32_t* status, uint32_t* newton_iters);
-/* Same solve, but only the time levels rows[0..n_rows) (strictly ascending, in [0, n_steps]; a host array) are stored:
+/* Same solve, but only the time levels rows[0..n_rows) (strictly ascending, in [0, n_steps]; host or device array) are stored:
  * g[N, n_rows, 12].  For consumers that down-sample in time -- posterior-predictive bands, the surrogate training
  * set of deeponet/generate_training_data.py:283-289 (np.linspace(0, T, n_time_out, dtype=int)). */
 int hmx_trajectory_rows(hmx_ctx* ctx, const double* theta, const int32_t* cond_id, int64_t N, const int32_t* rows,

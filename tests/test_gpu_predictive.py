@@ -58,3 +58,29 @@ def test_posterior_predictive_bands(built):
     data = np.array(cd["data"])
     inside = (data >= q[0][near] - 2 * cd["sigma_scalar"]) & (data <= q[2][near] + 2 * cd["sigma_scalar"])
     assert inside.mean() > 0.9
+
+
+@pytest.mark.gpu
+def test_trajectory_rows_accepts_a_device_row_list(built):
+    """hmx_trajectory_rows takes its row list from host or device memory (round-1 ABI rejected a device list at run time)."""
+    import torch
+
+    from tmcmc202601_b200 import _abi, workloads
+    from tmcmc202601_b200.engine import HamiltonEngine
+
+    wl = workloads.four_condition_workload(4, seed=2, solver=dict(workloads.PRODUCTION_SOLVER, maxtimestep=80))
+    for k in range(4):
+        for o, r in enumerate((5, 12, 30, 44, 60)):
+            wl.config.cond[k].idx_sparse[o] = r
+    eng = HamiltonEngine(wl.config, device=0)
+    try:
+        rows = np.array([0, 3, 40, 80], dtype=np.int32)
+        g_host, _, _ = eng.trajectory_rows(wl.theta, rows, wl.cond_id)
+        eng.use_torch_stream()
+        rows_d = torch.from_numpy(rows).cuda()
+        g = np.empty_like(g_host)
+        rc = eng._lib.hmx_trajectory_rows(eng._ctx, wl.theta.ctypes.data, wl.cond_id.ctypes.data, wl.theta.shape[0], rows_d.data_ptr(), rows.size,
+                                          g.ctypes.data, None, None)
+        assert rc == 0 and np.array_equal(g, g_host)
+    finally:
+        eng.close()

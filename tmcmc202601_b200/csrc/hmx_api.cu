@@ -805,7 +805,14 @@ int hmx_trajectory_rows(hmx_ctx* ctx, const double* theta, const int32_t* cond_i
     if (!g && N > 0) return fail(ctx, HMX_ERR_INVALID, "g is NULL");
     const int T = ctx->cfg.n_steps;
     if (!rows || n_rows < 1 || n_rows > T + 1) return fail(ctx, HMX_ERR_INVALID, "hmx_trajectory_rows: need 1 <= n_rows <= n_steps + 1");
-    if (is_device_ptr(rows)) return fail(ctx, HMX_ERR_INVALID, "hmx_trajectory_rows: rows must be a host array");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<int32_t> rows_host;
+    if (is_device_ptr(rows)) {  // a device row list is fetched (it is a handful of integers): the map is built on the host
+        rows_host.resize((size_t)n_rows);
+        CU(cudaMemcpyAsync(rows_host.data(), rows, (size_t)n_rows * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        rows = rows_host.data();
+    }
     std::string map((size_t)(T + 1) * sizeof(int32_t), '\0');
     int32_t* m = (int32_t*)&map[0];
     for (int t = 0; t <= T; ++t) m[t] = -1;
