@@ -143,7 +143,6 @@ HMX_HD bool lane_advance(const SolverConsts& K, Lane& s) {
 // convergence into a trip that also computes the next step's first direction.
 // x: the raw accepted trial (== s.g == new s.gp); gp5_old: phi_0 of the previous level before the advance.
 HMX_HD bool rebase_residual(const SolverConsts& K, const Lane& s, const double (&x)[12], double gp5_old, Eval& e) {
-    unsigned long long nb[6];
 #if defined(HMX_REBASE_FAST)
     // Common case: the accepted trial lies strictly inside the clip box, so clip(x) = x = the new previous level and the new
     // time derivatives are exactly zero: the update is "subtract the old time-derivative terms" (30 FP64 instructions fewer).
@@ -159,7 +158,6 @@ HMX_HD bool rebase_residual(const SolverConsts& K, const Lane& s, const double (
 #endif
             e.Q[i] = qi;
             e.Q[6 + i] = qs;
-            nb[i] = umax64(abs_bits(qi), abs_bits(qs));
         }
         e.Q[5] = e.Q[5] - (x[5] - gp5_old) * K.inv_dt;
     } else
@@ -178,19 +176,16 @@ HMX_HD bool rebase_residual(const SolverConsts& K, const Lane& s, const double (
             const double qs = e.Q[6 + i] + fma(e.p[i], dph, v * v * dps);
             e.Q[i] = qi;
             e.Q[6 + i] = qs;
-            nb[i] = umax64(abs_bits(qi), abs_bits(qs));
         }
         const double ph0 = clip01(x[5]);
         e.Q[5] = e.Q[5] + ((ph0 - s.gp[5]) - (ph0 - gp5_old)) * K.inv_dt;
     }
-    nb[5] = umax64(abs_bits(e.Q[5]), abs_bits(e.Q[11]));
-    const unsigned long long m = umax64(umax64(umax64(nb[0], nb[1]), umax64(nb[2], nb[3])), umax64(nb[4], nb[5]));
-    e.norm = bits_double(m);
-    e.nan = m > kInfBits;
+    bool finite;
+    norm12(e.Q, e.norm, e.nan, finite);
     // A non-finite component of x makes (clip(x) - x)/dt, hence a residual component, non-finite (gamma entered the
     // accepted residual itself, which was finite): this test doubles as the trajectory's isfinite scan (EV:657-667).
     // (On the in-box path every component of x is finite by the box test itself.)
-    return m < kInfBits;
+    return finite;
 }
 
 // One trip.  `step_end(g, gp, step_idx)` is called whenever the Newton loop of the current time step has ended,

@@ -134,6 +134,54 @@ HMX_HD double bits_double(unsigned long long u) {
 }
 HMX_HD unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
 
+// The same maximum with fewer issue slots (HMX_NORM_FP): the magnitude comparison is ONE DSETP with |.| operand modifiers and
+// the select picks the RAW value of larger magnitude (two SEL), so no absolute value is ever materialised; |.| is applied once
+// at the root.  Non-finite entries are detected by a 32-bit integer max tree over the high words (exponent all ones);
+// only then (never on the hot path) is the NaN test done entry by entry.  Values identical to the 64-bit integer tree.
+HMX_HD double larger_mag(double a, double b) { return (fabs(a) > fabs(b)) ? a : b; }
+HMX_HD uint32_t abs_hi(double a) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__double2hiint(a) & 0x7fffffffu;
+#else
+    unsigned long long u;
+    memcpy(&u, &a, sizeof(u));
+    return (uint32_t)(u >> 32) & 0x7fffffffu;
+#endif
+}
+HMX_HD uint32_t umax32(uint32_t a, uint32_t b) { return a > b ? a : b; }
+// ||Q||_inf, any(isnan(Q)) and all(isfinite(Q)) of the twelve residual entries
+HMX_HD void norm12(const double (&Q)[12], double& norm, bool& nan, bool& finite) {
+#if defined(HMX_NORM_FP)
+    const double m0 = larger_mag(larger_mag(Q[0], Q[6]), larger_mag(Q[1], Q[7]));
+    const double m1 = larger_mag(larger_mag(Q[2], Q[8]), larger_mag(Q[3], Q[9]));
+    const double m2 = larger_mag(larger_mag(Q[4], Q[10]), larger_mag(Q[5], Q[11]));
+    norm = fabs(larger_mag(larger_mag(m0, m1), m2));
+    const uint32_t h0 = umax32(umax32(abs_hi(Q[0]), abs_hi(Q[6])), umax32(abs_hi(Q[1]), abs_hi(Q[7])));
+    const uint32_t h1 = umax32(umax32(abs_hi(Q[2]), abs_hi(Q[8])), umax32(abs_hi(Q[3]), abs_hi(Q[9])));
+    const uint32_t h2 = umax32(umax32(abs_hi(Q[4]), abs_hi(Q[10])), umax32(abs_hi(Q[5]), abs_hi(Q[11])));
+    finite = umax32(umax32(h0, h1), h2) < 0x7ff00000u;
+    nan = false;
+    if (!finite) {  // rare: an inf or a NaN somewhere -- redo it with the exact semantics (a NaN makes the norm irrelevant)
+        double mx = 0.0;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            nan = nan || (Q[i] != Q[i]);
+            mx = (fabs(Q[i]) > mx) ? fabs(Q[i]) : mx;
+        }
+        norm = mx;
+    }
+#else
+    unsigned long long nb[6];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) nb[i] = umax64(abs_bits(Q[i]), abs_bits(Q[6 + i]));
+    nb[5] = umax64(abs_bits(Q[5]), abs_bits(Q[11]));
+    const unsigned long long m = umax64(umax64(umax64(nb[0], nb[1]), umax64(nb[2], nb[3])), umax64(nb[4], nb[5]));
+    norm = bits_double(m);  // a NaN pattern when a NaN is present: every comparison with it is false
+    nan = m > kInfBits;     // true for NaN only, +inf entries are not NaN (S5:342-348)
+    finite = m < kInfBits;
+#endif
+}
+
 // packed symmetric A: index of (i,j)
 HMX_HD constexpr int apk(int i, int j) {
     return (i <= j) ? (i * 5 - (i * (i - 1)) / 2 + (j - i)) : (j * 5 - (j * (j - 1)) / 2 + (i - j));
@@ -310,7 +358,6 @@ HMX_HD void residual(const SolverConsts& K, const double (&x)[12], const GPT& gp
         }
         e.I[4] *= e.h;
     }
-    unsigned long long nb[6];  // per-species max of |Q| as bit patterns: reduced as a tree to keep the dependency chain short
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
         const double v = e.ph[i], u = e.ps[i];
@@ -322,14 +369,11 @@ HMX_HD void residual(const SolverConsts& K, const double (&x)[12], const GPT& gp
         if (ALPHA) qs += (b[i] * K.alpha_eta[i]) * u;
         e.Q[i] = qi;
         e.Q[6 + i] = qs;
-        nb[i] = umax64(abs_bits(qi), abs_bits(qs));
     }
     e.Q[5] = gam + f0 + (ph0 - gp[5]) * K.inv_dt;                                  // S5:109-113
     e.Q[11] = ((((e.ph[0] + e.ph[1]) + e.ph[2]) + e.ph[3]) + e.ph[4]) + ph0 - 1.0;    // S5:126
-    nb[5] = umax64(abs_bits(e.Q[5]), abs_bits(e.Q[11]));
-    const unsigned long long m = umax64(umax64(umax64(nb[0], nb[1]), umax64(nb[2], nb[3])), umax64(nb[4], nb[5]));
-    e.norm = bits_double(m);  // ||Q||_inf (a NaN pattern when a NaN is present: every comparison with it is false)
-    e.nan = m > kInfBits;     // any(isnan(Q)): true for NaN only, +inf entries are not NaN (S5:342-348)
+    bool finite;
+    norm12(e.Q, e.norm, e.nan, finite);  // ||Q||_inf; any(isnan(Q)): true for NaN only, +inf entries are not NaN (S5:342-348)
 }
 
 // 5x5 solve with two right-hand sides.  S[r][0..4] matrix, S[r][5], S[r][6] the two right-hand sides ->
