@@ -246,3 +246,34 @@ def test_active_species_masks_against_live_reference_trajectories(built):
         assert np.array_equal(g[0], ref[0])
         rel = np.abs(g - ref) / np.maximum(np.abs(ref), 1e-300)
         assert rel.max() < 1e-9, (name, rel.max())
+
+
+def test_deviations_above_the_bar_only_where_the_reference_itself_is_ill_conditioned(engines):
+    """Outside the production settings (here dt = 1.18e-4, c = 50, non-unit eta: a configuration from the fuzz tool) some
+    time steps exhaust their 50 Newton iterations without contracting, and the result of such an evaluation depends on
+    rounding: the ORACLE's own value moves by up to 4e-5 when theta is perturbed by two ulps.  Parity at 1e-9 is undefined
+    there.  The statement that can be tested: wherever the GPU is further than 1e-9 from the oracle, the oracle is at least
+    1e-10 away from itself under a 2-ulp perturbation of its input -- and everywhere else the bar holds."""
+    solver = dict(dt=0.00011848512631842148, maxtimestep=500, c_const=50.0, alpha_const=0.0, Kp1=6.89941793513431e-05, K_hill=0.0, n_hill=2.0,
+                  eta_vec=[0.858, 1.068, 1.002, 1.164, 0.709], eta_phi_vec=[1.013, 0.956, 0.837, 1.116, 1.005])
+    n_far = 0
+    for seed in (1001, 1021, 1027):
+        wl = workloads.four_condition_workload(100, seed=seed, solver=solver)
+        rows = np.unique(np.linspace(500 // 8, 500, 5, dtype=int))
+        for c in range(4):
+            for o in range(5):
+                wl.config.cond[c].idx_sparse[o] = int(rows[o])
+        eng = engines(wl.config)
+        ll = eng.loglik_batch(wl.theta, wl.cond_id)
+        ref = orc.evaluate_hmx(wl.config, wl.theta, wl.cond_id)
+        sens = np.zeros_like(ref)
+        for k in range(3):  # three independent 2-ulp perturbations of every theta
+            sgn = np.sign(np.random.default_rng(k).standard_normal(wl.theta.shape))
+            sens = np.maximum(sens, _rel(orc.evaluate_hmx(wl.config, wl.theta * (1.0 + 4e-16 * sgn), wl.cond_id), ref))
+        rel = _rel(ll, ref)
+        far = rel > REL
+        n_far += int(far.sum())
+        print(f"seed {seed}: {int(far.sum())} of {rel.size} evaluations above 1e-9 (max {rel.max():.1e}); oracle self-sensitivity there >= {sens[far].min() if far.any() else 0:.1e}")
+        assert np.all(sens[far] > 1e-10), "a deviation above the bar where the reference is well conditioned"
+        assert np.all(rel[sens < 1e-13] < REL)
+    assert n_far >= 1  # the configuration was chosen because it has such evaluations
