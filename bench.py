@@ -261,6 +261,20 @@ def tmcmc_run():
                         "posterior_std_ratio": [cmp_["std_ratio_min"], cmp_["std_ratio_max"]], "logL_max": res["logL_max"]}
         except Exception as e:  # the throughput line must not be lost to a failure of the side measurement
             out[key] = {"error": f"{type(e).__name__}: {e}"}
+    # the two chains advanced concurrently with merged launches (batch.run_batch_TMCMC: bit-identical to running them one
+    # after the other, half the number of launches -- each launch costs the latency of its slowest solve)
+    try:
+        walls = []
+        for _ in range(2):
+            summ, res = rp.run_merged(["Dysbiotic_HOBIC_legacy_1k30"], 1000, 2, device_mutation=True)
+            walls.append(summ["wall_s"])
+        samples = np.concatenate(res[0]["chains"], axis=0)
+        cmp_ = rp.compare_with_reference(samples, np.concatenate(res[0]["logL"]))
+        out["device_mutation_merged_chains"] = {"wall_s": min(walls), "wall_s_first_run": walls[0], "merged_launches": summ["merged_launches"],
+                                                "likelihood_evaluations": summ["likelihood_evaluations"], "posterior_z_mean_max": cmp_["z_mean_max"],
+                                                "posterior_std_ratio": [cmp_["std_ratio_min"], cmp_["std_ratio_max"]]}
+    except Exception as e:  # noqa: BLE001
+        out["device_mutation_merged_chains"] = {"error": f"{type(e).__name__}: {e}"}
     return out
 
 

@@ -84,11 +84,12 @@ def run_merged(keys, n_particles, n_chains, seed=42, n_mutation_steps=5, n_stage
     jobs = []
     for key in keys:
         cd = conds[key]
+        legacy = key.endswith("legacy_1k30")  # the stored production run: phi_init = 0.02, scalar sigma, 6 observation rows
         base = np.full(20, 1.5)
         base[cd["locked"]] = 0.0
         jobs.append(dict(model_tag=f"{cd['condition']}_{cd['cultivation']}", data=cd["data"], idx_sparse=cd["idx_sparse"],
-                         sigma_obs=cd["sigma_obs"], phi_init=cd["phi_init"], prior_bounds=cd["bounds"], theta_base=base,
-                         active_indices=cd["active_indices"]))
+                         sigma_obs=cd["sigma_scalar"] if legacy else cd["sigma_obs"], phi_init=0.02 if legacy else cd["phi_init"],
+                         prior_bounds=cd["bounds"], theta_base=base, active_indices=cd["active_indices"]))
     out, stats = batch.run_batch_TMCMC(jobs, workloads.PRODUCTION_SOLVER, n_particles=n_particles, n_stages=n_stages,
                                        n_chains=n_chains, seed=seed, n_mutation_steps=n_mutation_steps, device_mutation=device_mutation)
     summary = {"mode": "merged", "device_mutation": bool(device_mutation), "conditions": list(keys), "n_particles": n_particles, "n_chains": n_chains, **stats,
