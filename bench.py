@@ -574,6 +574,9 @@ def main():
     th_h = torch.from_numpy(wl.theta).pin_memory().numpy()
     cid_h = torch.from_numpy(wl.cond_id).pin_memory().numpy()
     th_pop = eng.device_array((M, 20))
+    pop_n = world * N_PER_COND
+    pop_dev = eng.device_array(pop_n)  # the gathered population of one condition: uploaded once, read by three stage calls
+    w_dev = eng.device_array(pop_n)    # its normalised weights stay on the device (resampling and the covariance read them there)
 
     def host_step(step: int):
         th_pop.upload(th_h)                      # H2D theta (pinned source)
@@ -586,18 +589,18 @@ def main():
             full = logL.reshape(1, N_COND, N_PER_COND)
         out = None
         for c in range(N_COND):
-            pop = np.ascontiguousarray(full[:, c, :].reshape(-1))
-            db, _ = eng.beta_step(pop, 0.0, 0.5, 0.02, 0.5)
-            w, _ = eng.weights(pop, db)
-            idx = eng.resample(w, float(u_draw[(step * N_COND + c) % 1024]))
+            pop_dev.upload(np.ascontiguousarray(full[:, c, :].reshape(-1)))  # H2D population logL, once
+            db, _ = eng.beta_step(pop_dev, 0.0, 0.5, 0.02, 0.5)              # D2H two scalars
+            eng.weights_device(pop_dev, db, w_dev)                            # D2H log S_j
+            idx = eng.resample(w_dev, float(u_draw[(step * N_COND + c) % 1024]))  # D2H indices
             lo = c * N_PER_COND
-            w_loc = w[rank * N_PER_COND:(rank + 1) * N_PER_COND]
-            mom = eng.weighted_moments(th_pop[lo:lo + N_PER_COND], w_loc)
+            w_loc = w_dev[rank * N_PER_COND:(rank + 1) * N_PER_COND]
+            mom = eng.weighted_moments(th_pop[lo:lo + N_PER_COND], w_loc)     # D2H 22 moments
             if world > 1:
                 mt = torch.from_numpy(mom).to(dev)
                 dist.all_reduce(mt)
                 mom = mt.cpu().numpy()
-            sc = eng.weighted_scatter(th_pop[lo:lo + N_PER_COND], w_loc, mom[2:] / mom[0])
+            sc = eng.weighted_scatter(th_pop[lo:lo + N_PER_COND], w_loc, mom[2:] / mom[0])  # H2D mean, D2H 20 x 20
             if world > 1:
                 st = torch.from_numpy(sc).to(dev)
                 dist.all_reduce(st)
@@ -619,12 +622,10 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * M * e2e_steps / (float(te.item()) * 1e-3)
-    pop_n = world * N_PER_COND
-    # bytes the host-facing calls copy per step: theta (once) + cond_id in, logL out; per condition the population logL
-    # (beta_step, weights), w (resample), w_c twice (moments, scatter) and the mean in; w, idx, 3 scalars, 22 moments and
-    # the 20x20 scatter out
-    h2d = M * (20 * 8 + 4) + N_COND * (3 * pop_n * 8 + 2 * N_PER_COND * 8 + 20 * 8)
-    d2h = M * 8 + N_COND * (2 * pop_n * 8 + 3 * 8 + 22 * 8 + 400 * 8)
+    # bytes the host-facing calls copy per step: theta (once) + cond_id in, logL out; per condition the gathered population logL
+    # (once) and the 20-vector mean in; the resampling indices, 3 scalars, 22 moments and the 20 x 20 scatter out
+    h2d = M * (20 * 8 + 4) + N_COND * (pop_n * 8 + 20 * 8)
+    d2h = M * 8 + N_COND * (pop_n * 8 + 3 * 8 + 22 * 8 + 400 * 8)
 
     # ---- roofline of the dominant kernel (ode_kernel): executed FP64 flops / CUDA-event duration ---------
     ode_avg_ms = float(np.mean(ode_ms))
