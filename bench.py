@@ -17,8 +17,9 @@ A "step" is one pass of the hot path over one batch:
     systematic resampling, weighted covariance from shard-local partial sums + all-reduce).
 `value`  : inputs resident in HBM, timed with CUDA events on the launching stream, barrier + synchronize on
            both sides, max over ranks.
-`e2e`    : the same step through the public host-facing API (NumPy buffers: theta/cond_id H2D and
-           logL/weights/indices/covariance D2H inside the timed region).
+`e2e`    : the same step through the public host-facing API (theta/cond_id H2D from pinned NumPy buffers and
+           logL/indices/scalars/covariance D2H inside the timed region; the gathered log-likelihoods and the weights stay
+           on the device between the all-gather and the stage kernels).
 `roofline`: FP64 FMA pipe (the path is compute bound; HBM traffic is ~1.2 KB per 2e7-flop evaluation).
 `cpu_baseline` / `--impl reference`: the reference AS SHIPPED (kind "reference": oracle/_ref, a build-time snapshot of the
            reference's own evaluator modules written by oracle/make_ref.py, driven through its public API
@@ -575,26 +576,26 @@ def main():
     cid_h = torch.from_numpy(wl.cond_id).pin_memory().numpy()
     th_pop = eng.device_array((M, 20))
     pop_n = world * N_PER_COND
-    pop_dev = eng.device_array(pop_n)  # the gathered population of one condition: uploaded once, read by three stage calls
-    w_dev = eng.device_array(pop_n)    # its normalised weights stay on the device (resampling and the covariance read them there)
+    # results land in pinned host arrays (what a host program reads after the step): log-likelihoods of this rank's block and
+    # the resampling indices of the gathered population; the gathered log-likelihoods and the weights never leave the device
+    ll_h = torch.empty(M, dtype=torch.float64).pin_memory().numpy()
+    idx_h = torch.empty(pop_n, dtype=torch.int64).pin_memory().numpy()
+    mom_h, sc_h = np.empty(22), np.empty((20, 20))
 
     def host_step(step: int):
-        th_pop.upload(th_h)                      # H2D theta (pinned source)
-        logL = eng.loglik_batch(th_pop, cid_h)   # H2D cond_id, D2H logL
+        th_pop.upload(th_h)                                  # H2D theta (pinned source)
+        eng.loglik_batch_device(th_pop, cid_h, ll_d)         # H2D cond_id; logL stays on the device for the all-gather ...
+        torch.from_numpy(ll_h).copy_(ll_d)                   # ... and is read back: D2H logL (the step's result)
         if world > 1:
-            g = torch.from_numpy(logL).to(dev)
-            dist.all_gather_into_tensor(ll_all, g)
-            full = ll_all.cpu().numpy().reshape(world, N_COND, N_PER_COND)
-        else:
-            full = logL.reshape(1, N_COND, N_PER_COND)
+            dist.all_gather_into_tensor(ll_all, ll_d)
         out = None
         for c in range(N_COND):
-            pop_dev.upload(np.ascontiguousarray(full[:, c, :].reshape(-1)))  # H2D population logL, once
-            db, _ = eng.beta_step(pop_dev, 0.0, 0.5, 0.02, 0.5)              # D2H two scalars
-            eng.weights_device(pop_dev, db, w_dev)                            # D2H log S_j
-            idx = eng.resample(w_dev, float(u_draw[(step * N_COND + c) % 1024]))  # D2H indices
+            pop = ll_all[gather_idx[c]] if world > 1 else ll_d[c * N_PER_COND:(c + 1) * N_PER_COND]
+            db, _ = eng.beta_step(pop, 0.0, 0.5, 0.02, 0.5)                   # D2H two scalars
+            eng.weights_device(pop, db, w_d)                                  # D2H log S_j
+            eng.resample_device(w_d, float(u_draw[(step * N_COND + c) % 1024]), idx_h)  # D2H indices (pinned destination)
             lo = c * N_PER_COND
-            w_loc = w_dev[rank * N_PER_COND:(rank + 1) * N_PER_COND]
+            w_loc = w_d[rank * N_PER_COND:(rank + 1) * N_PER_COND]
             mom = eng.weighted_moments(th_pop[lo:lo + N_PER_COND], w_loc)     # D2H 22 moments
             if world > 1:
                 mt = torch.from_numpy(mom).to(dev)
@@ -605,7 +606,7 @@ def main():
                 st = torch.from_numpy(sc).to(dev)
                 dist.all_reduce(st)
                 sc = st.cpu().numpy()
-            out = (idx, sc)
+            out = (idx_h, sc)
         return out
 
     host_step(0)
@@ -622,10 +623,10 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * M * e2e_steps / (float(te.item()) * 1e-3)
-    # bytes the host-facing calls copy per step: theta (once) + cond_id in, logL out; per condition the gathered population logL
-    # (once) and the 20-vector mean in; the resampling indices, 3 scalars, 22 moments and the 20 x 20 scatter out
-    h2d = M * (20 * 8 + 4) + N_COND * (pop_n * 8 + 20 * 8)
-    d2h = M * 8 + N_COND * (pop_n * 8 + 3 * 8 + 22 * 8 + 400 * 8)
+    # bytes the host-facing calls copy per step: theta + cond_id in, logL out; per condition the 20-vector mean in (and, on
+    # several GPUs, the all-reduced moments / scatter); the resampling indices, 3 scalars, 22 moments and the 20 x 20 scatter out
+    h2d = M * (20 * 8 + 4) + N_COND * (20 * 8 + (0 if world == 1 else (22 + 400) * 8))
+    d2h = M * 8 + N_COND * (pop_n * 8 + 3 * 8 + (22 + 400) * 8 * (1 if world == 1 else 2))
 
     # ---- roofline of the dominant kernel (ode_kernel): executed FP64 flops / CUDA-event duration ---------
     ode_avg_ms = float(np.mean(ode_ms))

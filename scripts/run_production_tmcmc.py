@@ -76,7 +76,7 @@ def compare_with_reference(samples, ll):
             "reference_elapsed_s": 226864.8}
 
 
-def run_merged(keys, n_particles, n_chains, seed=42, n_mutation_steps=5, n_stages=30, device_mutation=False):
+def run_merged(keys, n_particles, n_chains, seed=42, n_mutation_steps=5, n_stages=30, device_mutation=False, merge_launches=True):
     """All conditions x chains concurrently, likelihood launches merged (tmcmc202601_b200.batch)."""
     from tmcmc202601_b200 import batch
 
@@ -91,8 +91,9 @@ def run_merged(keys, n_particles, n_chains, seed=42, n_mutation_steps=5, n_stage
                          sigma_obs=cd["sigma_scalar"] if legacy else cd["sigma_obs"], phi_init=0.02 if legacy else cd["phi_init"],
                          prior_bounds=cd["bounds"], theta_base=base, active_indices=cd["active_indices"]))
     out, stats = batch.run_batch_TMCMC(jobs, workloads.PRODUCTION_SOLVER, n_particles=n_particles, n_stages=n_stages,
-                                       n_chains=n_chains, seed=seed, n_mutation_steps=n_mutation_steps, device_mutation=device_mutation)
-    summary = {"mode": "merged", "device_mutation": bool(device_mutation), "conditions": list(keys), "n_particles": n_particles, "n_chains": n_chains, **stats,
+                                       n_chains=n_chains, seed=seed, n_mutation_steps=n_mutation_steps, device_mutation=device_mutation,
+                                       merge_launches=merge_launches)
+    summary = {"mode": "merged" if merge_launches else "own stream per chain", "device_mutation": bool(device_mutation), "conditions": list(keys), "n_particles": n_particles, "n_chains": n_chains, **stats,
                "per_condition": [{"condition": k, "converged": o["converged"], "stages": [len(r.stage_summary) for r in o["results"]],
                                   "logL_max": float(max(l.max() for l in o["logL"]))} for k, o in zip(keys, out)]}
     return summary, out

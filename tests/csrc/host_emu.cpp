@@ -136,6 +136,24 @@ static void run_reference_loop(const SolverConsts& K, const CondConsts& C, const
     *iters = it;
 }
 
+// per-trip event trace of one lane (scripts/trip_sim.py): bit0 = a direction was solved, bit1 = the time step ended
+template <bool ALPHA, int HILL>
+static void trace_lane(const SolverConsts& K, const CondConsts& C, const double* theta, uint8_t* ev, long long cap, long long* n_out) {
+    Lane s;
+    lane_init(K, s, theta, C.g0);
+    auto step_end = [&](const double (&)[12], const LaneGP&, int) {};
+    long long n = 0;
+    bool done = false;
+    while (!done) {
+        const uint32_t it0 = s.iters;
+        const int32_t st0 = s.step_idx;
+        done = lane_trip<ALPHA, HILL>(K, s, step_end);
+        if (n < cap) ev[n] = (uint8_t)((s.iters != it0 ? 1 : 0) | (s.step_idx != st0 ? 2 : 0));
+        ++n;
+    }
+    *n_out = n;
+}
+
 extern "C" {
 
 // hmx_dense.cuh on the CPU: the reference's loop nest with the dense pivoted solve + ridge retry; g_arr [(n_steps + 1), 12]
@@ -193,6 +211,15 @@ int emu_sensitivities(const hmx_config* cfg, const double* theta, const double* 
 }
 int emu_sizeof_legacy_config(void) { return (int)sizeof(hmx_legacy_config); }
 
+
+int emu_trip_trace(const hmx_config* cfg, int cond, const double* theta, uint8_t* ev, long long cap, long long* n_out) {
+    SolverConsts K;
+    CondConsts C;
+    make_solver_consts(*cfg, K);
+    make_cond_consts(*cfg, cond, C);
+    DISPATCH(trace_lane, K, C, theta, ev, cap, n_out);
+    return 0;
+}
 
 // full solve of one (theta, condition): trajectory (optional), logL, counters
 int emu_evaluate(const hmx_config* cfg, int cond, const double* theta, double* g_arr, double* logL,

@@ -78,3 +78,18 @@ def test_merged_device_mutation_equals_independent_chains():
             assert np.array_equal(solo.samples, out[k]["chains"][chain])
             assert np.array_equal(solo.logL_values, out[k]["logL"][chain])
             assert solo.acc_rate_history == out[k]["results"][chain].acc_rate_history
+
+
+def test_unmerged_streams_mode_equals_merged():
+    """merge_launches=False (every chain on its own context / stream) returns the samples of the merged run bit for bit and
+    counts one launch per chain and round instead of one per round."""
+    jobs = _jobs()
+    kw = dict(n_particles=24, n_stages=4, n_chains=2, seed=7, n_mutation_steps=2, stage_ops=OracleStageOps(),
+              engine_factory=lambda cfg: OracleEngine(cfg, n_threads=4), device_mutation=True)
+    merged, ms = batch.run_batch_TMCMC(jobs, SOLVER, **kw)
+    free, fs = batch.run_batch_TMCMC(jobs, SOLVER, merge_launches=False, **kw)
+    assert fs["likelihood_evaluations"] == ms["likelihood_evaluations"] and fs["merged_launches"] > ms["merged_launches"]
+    for a, b in zip(merged, free):
+        for chain in range(2):
+            assert np.array_equal(a["chains"][chain], b["chains"][chain])
+            assert np.array_equal(a["logL"][chain], b["logL"][chain])

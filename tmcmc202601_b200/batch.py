@@ -133,6 +133,47 @@ class _BrokerEngine:
         pass
 
 
+class _Tally:
+    """Launch / evaluation counters of the unmerged mode (what the broker reports in the merged one)."""
+
+    def __init__(self):
+        self.lock = threading.Lock()
+        self.launches = 0
+        self.evaluations = 0
+        self.gpu_seconds = 0.0
+
+    def add(self, n, dt):
+        with self.lock:
+            self.launches += 1
+            self.evaluations += int(n)
+            self.gpu_seconds += dt
+
+    def client_done(self):
+        pass
+
+
+class _CountingEngine:
+    """A chain's own engine in the unmerged mode; forwards everything, counts launches and evaluations."""
+
+    def __init__(self, inner, tally: _Tally):
+        self.inner, self._tally = inner, tally
+
+    def __getattr__(self, name):
+        return getattr(self.inner, name)
+
+    def loglik_batch(self, theta, *a, **k):
+        t0 = time.perf_counter()
+        out = self.inner.loglik_batch(theta, *a, **k)
+        self._tally.add(np.shape(theta)[0], time.perf_counter() - t0)
+        return out
+
+    def mutate(self, mutation, theta_res, *a, **k):
+        t0 = time.perf_counter()
+        out = self.inner.mutate(mutation, theta_res, *a, **k)
+        self._tally.add(np.shape(theta_res)[0] * mutation.K, time.perf_counter() - t0)
+        return out
+
+
 class _LockedStageOps:
     """Stage kernels on one shared context; calls from the chain threads are serialised."""
 
@@ -158,13 +199,18 @@ class _LockedStageOps:
 
 def run_batch_TMCMC(jobs: Sequence[Dict[str, Any]], solver_kwargs: Dict[str, Any], n_particles: int = 1000, n_stages: int = 30,
                     n_chains: int = 2, seed: int = 42, n_mutation_steps: int = 5, min_delta_beta: float = 0.02,
-                    max_delta_beta: float = 0.5, device: int = 0, stage_ops=None, engine_factory=None, device_mutation: bool = False):
+                    max_delta_beta: float = 0.5, device: int = 0, stage_ops=None, engine_factory=None, device_mutation: bool = False,
+                    merge_launches: bool = True):
     """Run len(jobs) x n_chains TMCMC chains concurrently on one GPU.
 
     jobs[k] needs: model_tag, data, idx_sparse, sigma_obs, phi_init, prior_bounds, theta_base, active_indices
     (optional: cov_rel=0.005, weights, use_absolute_volume).  All jobs share `solver_kwargs` (without phi_init).
     Returns one dict per job with the same five entries run_multi_chain_TMCMC returns, plus broker statistics.
     `device_mutation=True`: the chains' mutation steps are merged as well (hmx_mutate_groups: one group per chain).
+    `merge_launches=False`: no broker -- every chain owns a context (its own CUDA stream) and launches as soon as it is ready,
+    so a chain waiting for the slowest solve of its stage no longer holds the other chains back: the kernels of different
+    chains share the GPU.  Same samples (a likelihood does not depend on the launch it travels in); pays off when the
+    chains need different numbers of stages or when a merged launch would exceed one resident round of lanes.
     """
     if not 1 <= len(jobs) <= _abi.MAX_COND // 2:
         raise ValueError(f"between 1 and {_abi.MAX_COND // 2} jobs per GPU context")
@@ -176,11 +222,14 @@ def run_batch_TMCMC(jobs: Sequence[Dict[str, Any]], solver_kwargs: Dict[str, Any
                                         active_theta_indices=[i for i in j["active_indices"] if i < _abi.NTHETA],
                                         weights=j.get("weights"), use_absolute_volume=j.get("use_absolute_volume", False),
                                         tsm_variance=tsm))
-    cfg = _abi.make_config(conds, **kw)
-    engine = engine_factory(cfg) if engine_factory else HamiltonEngine(cfg, device=device)
-    lock = threading.Lock()
-    broker = MergedLikelihoodBroker(engine, len(jobs) * n_chains, engine_lock=lock)
-    ops = _LockedStageOps(stage_ops if stage_ops is not None else tmcmc.GpuStageOps(engine=engine), lock)
+    if merge_launches:
+        cfg = _abi.make_config(conds, **kw)
+        engine = engine_factory(cfg) if engine_factory else HamiltonEngine(cfg, device=device)
+        lock = threading.Lock()
+        broker = MergedLikelihoodBroker(engine, len(jobs) * n_chains, engine_lock=lock)
+        ops = _LockedStageOps(stage_ops if stage_ops is not None else tmcmc.GpuStageOps(engine=engine), lock)
+    else:
+        engine, broker, ops = None, _Tally(), stage_ops
     results: List[List[Optional[tmcmc.TMCMCResult]]] = [[None] * n_chains for _ in jobs]
     errors: List[BaseException] = []
 
@@ -191,13 +240,18 @@ def run_batch_TMCMC(jobs: Sequence[Dict[str, Any]], solver_kwargs: Dict[str, Any
                                         np.asarray(j["theta_base"], float), j["data"], j["idx_sparse"], j["sigma_obs"],
                                         cov_rel=j.get("cov_rel", 0.005), theta_linearization=np.asarray(j["theta_base"], float),
                                         weights=j.get("weights"), use_absolute_volume=j.get("use_absolute_volume", False),
-                                        engine_factory=lambda _cfg, k=k: _BrokerEngine(broker, k))
+                                        engine_factory=(lambda _cfg, k=k: _BrokerEngine(broker, k)) if merge_launches else
+                                        ((lambda c: _CountingEngine(engine_factory(c), broker)) if engine_factory else
+                                         (lambda c: _CountingEngine(HamiltonEngine(c, device=device), broker))))
+            my_ops = ops if ops is not None else tmcmc.GpuStageOps(engine=ev._engine.inner)
             chain_seed = (int(seed or 0) + tmcmc._stable_hash_int(j["model_tag"]) % (2**31) + n_chains * 1000 + chain) % (2**31)
             results[k][chain] = tmcmc.run_TMCMC(
                 log_likelihood=ev, prior_bounds=[tuple(b) for b in j["prior_bounds"]], n_particles=n_particles, n_stages=n_stages,
                 min_delta_beta=min_delta_beta, max_delta_beta=max_delta_beta, seed=chain_seed,
                 model_name=f"{j['model_tag']}_chain{chain + 1}", evaluator=ev, theta_base_full=np.asarray(j["theta_base"], float),
-                active_indices=list(j["active_indices"]), n_mutation_steps=n_mutation_steps, stage_ops=ops, device_mutation=device_mutation)
+                active_indices=list(j["active_indices"]), n_mutation_steps=n_mutation_steps, stage_ops=my_ops, device_mutation=device_mutation)
+            if not merge_launches:
+                ev.close()
         except BaseException as e:  # noqa: BLE001 - reported to the caller after all threads stopped
             errors.append(e)
         finally:
@@ -224,6 +278,6 @@ def run_batch_TMCMC(jobs: Sequence[Dict[str, Any]], solver_kwargs: Dict[str, Any
         })
     stats = {"wall_s": wall, "merged_launches": broker.launches, "likelihood_evaluations": broker.evaluations,
              "likelihood_wall_s": broker.gpu_seconds}
-    if not engine_factory:
+    if engine is not None and not engine_factory:
         engine.close()
     return out, stats
