@@ -107,16 +107,38 @@ int fail(hmx_ctx* ctx, int code, const std::string& msg) {
             return fail(ctx, HMX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
     } while (0)
 
+// Scratch buffers come from the stream-ordered allocator: cudaMalloc / cudaFree synchronise the whole DEVICE, so a context
+// growing (or releasing) a buffer would wait for -- and, holding the driver's lock, stall -- the kernels of every other
+// context on the GPU (chains on their own streams, run_batch_TMCMC(merge_launches=False)).  cudaMallocAsync / cudaFreeAsync
+// are ordered on the context's stream only.
+cudaError_t dev_alloc(hmx_ctx* ctx, void** p, size_t bytes) {
+    cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+    if (e == cudaErrorNotSupported) {
+        cudaGetLastError();
+        e = cudaMalloc(p, bytes);
+    }
+    return e;
+}
+
+void dev_free(hmx_ctx* ctx, void* p) {
+    if (!p) return;
+    if (cudaFreeAsync(p, ctx->stream) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(p);
+    }
+}
+
 int ensure(hmx_ctx* ctx, DevBuf& b, size_t bytes) {
     if (bytes <= b.cap) return 0;
-    if (b.p) cudaFree(b.p);
+    dev_free(ctx, b.p);  // ordered after the work already queued on the stream that may still read it
     b.p = nullptr;
     b.cap = 0;
     size_t want = bytes + bytes / 8 + 256;
-    cudaError_t e = cudaMalloc(&b.p, want);
+    cudaError_t e = dev_alloc(ctx, &b.p, want);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        return fail(ctx, HMX_ERR_OOM, std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e));
+        b.p = nullptr;
+        return fail(ctx, HMX_ERR_OOM, std::string("cudaMallocAsync(") + std::to_string(want) + "): " + cudaGetErrorString(e));
     }
     b.cap = want;
     return 0;
@@ -543,18 +565,20 @@ int hmx_create(hmx_ctx** out, const hmx_config* cfg, int32_t device) {
     CU_CREATE(cudaSetDevice(device));
     CU_CREATE(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
-    CU_CREATE(cudaMalloc((void**)&ctx->d_cond, sizeof(CondConsts) * HMX_MAX_COND));
-    CU_CREATE(cudaMemcpy(ctx->d_cond, ctx->C, sizeof(CondConsts) * HMX_MAX_COND, cudaMemcpyHostToDevice));
-    CU_CREATE(cudaMalloc((void**)&ctx->d_counters, 20 * sizeof(unsigned long long)));
-    CU_CREATE(cudaMemset(ctx->d_counters, 0, 20 * sizeof(unsigned long long)));
-    CU_CREATE(cudaMalloc((void**)&ctx->d_sched, sizeof(SchedState)));
-    CU_CREATE(cudaMemset(ctx->d_sched, 0, sizeof(SchedState)));
-    CU_CREATE(cudaMalloc((void**)&ctx->d_stage, sizeof(StageState)));
-    CU_CREATE(cudaMemset(ctx->d_stage, 0, sizeof(StageState)));
-    CU_CREATE(cudaMalloc((void**)&ctx->d_tickets, 64 * sizeof(unsigned int)));
-    CU_CREATE(cudaMemset(ctx->d_tickets, 0, 64 * sizeof(unsigned int)));
-    CU_CREATE(cudaMalloc((void**)&ctx->d_mut_counts, 8 * kMutMaxGroups * sizeof(unsigned long long)));
-    CU_CREATE(cudaMalloc((void**)&ctx->d_small, 4096 * sizeof(double)));
+    // small per-context state, stream-ordered like the scratch buffers (no device-wide synchronisation: see dev_alloc)
+    CU_CREATE(dev_alloc(ctx, (void**)&ctx->d_cond, sizeof(CondConsts) * HMX_MAX_COND));
+    CU_CREATE(cudaMemcpyAsync(ctx->d_cond, ctx->C, sizeof(CondConsts) * HMX_MAX_COND, cudaMemcpyHostToDevice, ctx->stream));
+    CU_CREATE(dev_alloc(ctx, (void**)&ctx->d_counters, 20 * sizeof(unsigned long long)));
+    CU_CREATE(cudaMemsetAsync(ctx->d_counters, 0, 20 * sizeof(unsigned long long), ctx->stream));
+    CU_CREATE(dev_alloc(ctx, (void**)&ctx->d_sched, sizeof(SchedState)));
+    CU_CREATE(cudaMemsetAsync(ctx->d_sched, 0, sizeof(SchedState), ctx->stream));
+    CU_CREATE(dev_alloc(ctx, (void**)&ctx->d_stage, sizeof(StageState)));
+    CU_CREATE(cudaMemsetAsync(ctx->d_stage, 0, sizeof(StageState), ctx->stream));
+    CU_CREATE(dev_alloc(ctx, (void**)&ctx->d_tickets, 64 * sizeof(unsigned int)));
+    CU_CREATE(cudaMemsetAsync(ctx->d_tickets, 0, 64 * sizeof(unsigned int), ctx->stream));
+    CU_CREATE(dev_alloc(ctx, (void**)&ctx->d_mut_counts, 8 * kMutMaxGroups * sizeof(unsigned long long)));
+    CU_CREATE(dev_alloc(ctx, (void**)&ctx->d_small, 4096 * sizeof(double)));
+    CU_CREATE(cudaStreamSynchronize(ctx->stream));
     CU_CREATE(cudaEventCreate(&ctx->ev0));
     CU_CREATE(cudaEventCreate(&ctx->ev1));
     ctx->ode_blocks_per_sm = query_occupancy(ctx);
@@ -583,16 +607,11 @@ void hmx_destroy(hmx_ctx* ctx) {
                       &ctx->partial, &ctx->cs, &ctx->order, &ctx->m_props, &ctx->m_theta, &ctx->m_cond, &ctx->m_inside,
                       &ctx->m_ll, &ctx->m_status, &ctx->m_in_theta, &ctx->m_in_logL, &ctx->m_out_theta, &ctx->m_out_logL, &ctx->row_map, &ctx->m_groups, &ctx->logL_scratch,
                       &ctx->g_traj, &ctx->g_pull, &ctx->g_grad, &ctx->g_dstate, &ctx->cs_info};
-    for (DevBuf* b : bufs)
-        if (b->p) cudaFree(b->p);
+    for (DevBuf* b : bufs) dev_free(ctx, b->p);
+    void* small[] = {ctx->d_cond, ctx->d_counters, ctx->d_sched, ctx->d_stage, ctx->d_tickets, ctx->d_mut_counts, ctx->d_small};
+    for (void* q : small) dev_free(ctx, q);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (void* p : ctx->populations) cudaFree(p);
-    if (ctx->d_cond) cudaFree(ctx->d_cond);
-    if (ctx->d_counters) cudaFree(ctx->d_counters);
-    if (ctx->d_sched) cudaFree(ctx->d_sched);
-    if (ctx->d_stage) cudaFree(ctx->d_stage);
-    if (ctx->d_tickets) cudaFree(ctx->d_tickets);
-    if (ctx->d_mut_counts) cudaFree(ctx->d_mut_counts);
-    if (ctx->d_small) cudaFree(ctx->d_small);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -648,7 +667,14 @@ int hmx_population_download(hmx_ctx* ctx, double* host, const double* dev, int64
 
 int hmx_set_stream(hmx_ctx* ctx, void* cuda_stream) {
     if (!ctx) return HMX_ERR_INVALID;
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    cudaStream_t next = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    if (next != ctx->stream) {
+        // scratch buffers are allocated (and released) in stream order: drain the old stream so that everything it allocated
+        // is complete memory for the new one
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->stream = next;
     return HMX_OK;
 }
 
