@@ -143,9 +143,24 @@ def reference_as_shipped(wl, n_cond_sample: int = 1) -> dict | None:
     t0 = time.perf_counter()
     arm.evaluate(wl.theta[sel], wl.cond_id[sel])
     dt = time.perf_counter() - t0
-    return {"value": sel.size / dt, "unit": UNIT, "cores": cores, "kind": "reference",
-            "sample": f"{sel.size} evaluations (condition(s) {conds}) through the reference's LogLikelihoodEvaluator + "
-                      f"evaluate_particles_parallel(n_jobs={cores}) from oracle/_ref, {dt:.1f} s after a {t_warm:.1f} s warm-up (numba JIT)"}
+    out = {"value": sel.size / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+           "sample": f"{sel.size} evaluations (condition(s) {conds}) through the reference's LogLikelihoodEvaluator + "
+                     f"evaluate_particles_parallel(n_jobs={cores}) from oracle/_ref, {dt:.1f} s after a {t_warm:.1f} s warm-up (numba JIT)"}
+    # the reference without its Python sensitivity loop -- its numba solve + its log_likelihood_sparse with
+    # sig = 0, particles over forked workers (not the same quantity as `value`: the TSM variance is off)
+    try:
+        per = 16 * cores // N_COND
+        sel2 = np.concatenate([np.nonzero(wl.cond_id == c)[0][:per] for c in range(N_COND)])
+        arm.warm_up_ode_only(wl.theta[sel2], wl.cond_id[sel2])
+        t0 = time.perf_counter()
+        arm.evaluate_ode_only(wl.theta[sel2], wl.cond_id[sel2])
+        dt2 = time.perf_counter() - t0
+        out["reference_ode_only"] = {"value": sel2.size / dt2, "unit": UNIT, "cores": cores,
+                                     "sample": f"{sel2.size} evaluations ({per} per condition), BiofilmNewtonSolver5S.run_deterministic + "
+                                               f"log_likelihood_sparse(sig=0) from oracle/_ref on {cores} forked workers, {dt2:.1f} s"}
+    except Exception as e:  # noqa: BLE001
+        out["reference_ode_only"] = {"error": f"{type(e).__name__}: {e}"}
+    return out
 
 
 def cpu_baseline(wl, budget_s: float = 12.0, max_evals: int = 16384) -> dict:

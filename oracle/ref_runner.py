@@ -77,3 +77,50 @@ class ReferenceArm:
             sub = theta_full[sel][:, self.active[c]]  # EV:635-637 scatters theta_sub[i] to full[active[i]]
             out[sel] = self._parallel(self.evaluators[c], sub, n_jobs=min(self.n_jobs, sel.size) if sel.size > 1 else 1)
         return out
+
+    # ---- the reference WITHOUT its Python sensitivity loop -------------------------------------------
+    def _ode_only_one(self, c, theta_full):
+        """The reference's numba solve + its own log_likelihood_sparse with sig = 0 (EV:568, 698-745 with the variance off)."""
+        import sys
+
+        ev = self.evaluators[c]
+        lls = sys.modules[type(ev).__module__].log_likelihood_sparse
+        _, x0 = ev.solver.run_deterministic(np.asarray(theta_full, dtype=np.float64))
+        if not np.all(np.isfinite(x0)):
+            return -1e20
+        idx = np.asarray(ev.idx_sparse)
+        ns = (x0.shape[1] - 2) // 2
+        other = x0[idx, -1][:, None] if ev.use_absolute_volume else x0[idx][:, ns + 1:2 * ns + 1]
+        mu = x0[idx][:, :ns] * other
+        return float(lls(mu, np.zeros_like(mu), ev.data, ev.sigma_obs, rho=0.0, weights=ev.weights))
+
+    def evaluate_ode_only(self, theta_full, cond_id):
+        """logL[n] with the TSM variance off, particles mapped over forked worker processes (the compiled numba code of the
+        parent is inherited, so call warm_up_ode_only first)."""
+        import multiprocessing as mp
+
+        global _ODE_ARM
+        theta_full = np.asarray(theta_full, dtype=np.float64)
+        _ODE_ARM = self
+        tasks = [(int(c), theta_full[i]) for i, c in enumerate(cond_id)]
+        n = min(self.n_jobs, len(tasks))
+        if n <= 1:
+            return np.array([_ode_task(t) for t in tasks])
+        with mp.get_context("fork").Pool(n) as pool:
+            return np.array(pool.map(_ode_task, tasks, chunksize=max(1, len(tasks) // (4 * n))))
+
+    def warm_up_ode_only(self, theta_full, cond_id):
+        t0 = time.perf_counter()
+        for c in range(len(self.evaluators)):
+            sel = np.nonzero(cond_id == c)[0]
+            if sel.size:
+                self._ode_only_one(c, theta_full[sel[0]])
+        return time.perf_counter() - t0
+
+
+_ODE_ARM = None
+
+
+def _ode_task(task):
+    c, th = task
+    return _ODE_ARM._ode_only_one(c, th)

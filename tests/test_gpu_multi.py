@@ -48,3 +48,62 @@ def test_multi_handle_shards_a_host_batch(built):
             MultiEngine(wl.config, [0, 4096])
     finally:
         single.close()
+
+
+def test_contexts_on_their_own_streams_run_side_by_side(built):
+    """Several contexts on ONE device, driven from host threads (run_batch_TMCMC(merge_launches=False)): results are bitwise
+    those of a single context, also while the contexts grow and release their scratch buffers next to each other's running
+    kernels (the buffers come from the stream-ordered allocator, so nothing synchronises the device)."""
+    import threading
+
+    from tmcmc202601_b200.engine import HamiltonEngine
+
+    wl = workloads.four_condition_workload(64, seed=5, interleave=True)
+    single = HamiltonEngine(wl.config, device=0)
+    ref = single.loglik_batch(wl.theta, wl.cond_id)
+    single.close()
+    out, errs = {}, []
+
+    def work(k):
+        try:
+            eng = HamiltonEngine(wl.config, device=0)
+            for n in (16, 256, 40, 256):  # growing and re-used scratch
+                out[(k, n)] = eng.loglik_batch(wl.theta[:n], wl.cond_id[:n])
+            w = np.full(256, 1.0 / 256)
+            out[(k, "idx")] = eng.resample(w, 0.25)
+            eng.close()
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    for k in range(4):
+        for n in (16, 256, 40):
+            assert np.array_equal(out[(k, n)], ref[:n])
+        assert np.array_equal(out[(k, "idx")], np.arange(256))
+
+
+def test_stream_switch_keeps_scratch_valid(built):
+    """hmx_set_stream after buffers were allocated on the context's own stream: the old stream is drained, later growth and
+    release happen in the new stream's order; values unchanged."""
+    import torch
+
+    from tmcmc202601_b200.engine import HamiltonEngine
+
+    wl = workloads.four_condition_workload(48, seed=9)
+    eng = HamiltonEngine(wl.config, device=0)
+    try:
+        a = eng.loglik_batch(wl.theta[:32], wl.cond_id[:32])
+        eng.use_torch_stream()
+        th = torch.from_numpy(wl.theta).cuda()
+        cid = torch.from_numpy(wl.cond_id).cuda()
+        ll = torch.empty(th.shape[0], dtype=torch.float64, device="cuda")
+        eng.loglik_batch_device(th, cid, ll)  # larger batch: every scratch buffer grows on the new stream
+        torch.cuda.synchronize()
+        b = ll.cpu().numpy()
+        assert np.array_equal(b[:32], a)
+        assert np.array_equal(eng.loglik_batch(wl.theta, wl.cond_id), b)
+    finally:
+        eng.close()
