@@ -97,6 +97,11 @@ __global__ void HMX_ODE_BOUNDS ode_kernel(const __grid_constant__ OdeParams P) {
     static_assert(HMX_STASH_IN_SMEM == kOdeThreads, "HMX_STASH_IN_SMEM must equal the ODE block size");
     s.stash.p = smStash + threadIdx.x;
 #endif
+#if defined(HMX_D_IN_SMEM) && !defined(HMX_STATE_IN_SMEM)
+    __shared__ double smD[12 * kOdeThreads];
+    static_assert(HMX_D_IN_SMEM == kOdeThreads, "HMX_D_IN_SMEM must equal the ODE block size");
+    s.d.p = smD + threadIdx.x;
+#endif
 #if defined(HMX_STATE_IN_SMEM)
     __shared__ double smGP[11 * kOdeThreads];
     __shared__ double smD[12 * kOdeThreads];

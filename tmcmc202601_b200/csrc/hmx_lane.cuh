@@ -58,7 +58,11 @@ struct RegArr {
     HMX_HD const double& operator[](int k) const { return v[k]; }
 };
 using LaneGP = RegArr<11>;
+#if defined(HMX_D_IN_SMEM) && defined(__CUDACC__)
+using LaneD = SmemCol<HMX_D_IN_SMEM>;  // the Newton direction alone (written once, read once per trip): 24 registers freed
+#else
 using LaneD = RegArr<12>;
+#endif
 #endif
 
 #if defined(HMX_STASH_IN_SMEM) && defined(__CUDACC__)
