@@ -154,7 +154,36 @@ static void trace_lane(const SolverConsts& K, const CondConsts& C, const double*
     *n_out = n;
 }
 
+// tsm_row of hmx_obs.cuh (factor once, one solve per active parameter) on one trajectory row
+template <bool ALPHA, int HILL>
+static void tsm_row_once(const SolverConsts& K, const CondConsts& C, const double* theta, const double* g_new, const double* g_old,
+                         double* sig2_out, double* x1_out, int* ok) {
+    ThetaMap tm = {HMX_THETA_P, HMX_THETA_Q};
+    double A[15], b[5], x[12], gp[11], sig2[12], covp[5];
+    theta_to_Ab(theta, A, b);
+    for (int i = 0; i < 12; ++i) x[i] = g_new[i];
+    for (int i = 0; i < 11; ++i) gp[i] = g_old[i];
+    for (int i = 0; i < 12; ++i) sig2[i] = 0.0;
+    for (int i = 0; i < 5; ++i) covp[i] = 0.0;
+    for (int i = 0; i < 12 * HMX_NTHETA; ++i) x1_out[i] = 0.0;
+    *ok = tsm_row<ALPHA, HILL>(K, C, tm, theta, A, b, x, gp, sig2, covp, x1_out) ? 1 : 0;
+    for (int i = 0; i < 12; ++i) sig2_out[i] = sig2[i];
+}
+
 extern "C" {
+
+// sigma2[12] and x1[12,20] of one trajectory row through the product's tsm_row (hmx_obs.cuh)
+int emu_tsm_row(const hmx_config* cfg, int cond, const double* theta, const double* g_new, const double* g_old, double* sig2,
+                double* x1) {
+    SolverConsts K;
+    CondConsts C;
+    make_solver_consts(*cfg, K);
+    make_cond_consts(*cfg, cond, C);
+    int ok = 0;
+    DISPATCH(tsm_row_once, K, C, theta, g_new, g_old, sig2, x1, &ok);
+    return ok;
+}
+
 
 // hmx_dense.cuh on the CPU: the reference's loop nest with the dense pivoted solve + ridge retry; g_arr [(n_steps + 1), 12]
 int emu_reference_loop(const hmx_config* cfg, int cond, const double* theta, double* g_arr, uint32_t* status, uint32_t* iters) {

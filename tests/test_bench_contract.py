@@ -56,17 +56,24 @@ def test_gpu_arm_refuses_to_run_without_a_gpu():
 
 def test_reference_ode_only_baseline_equals_the_oracle():
     """SURVEY 8(d)(ii), the reference without its Python sensitivity loop (its numba solve + its log_likelihood_sparse with
-    sig = 0, oracle/ref_runner.py): one more pin of the oracle, and the number bench.py reports as `reference_ode_only`."""
-    import numpy as np
-
+    sig = 0, oracle/ref_runner.py): one more pin of the oracle, and the number bench.py reports as `reference_ode_only`.
+    Runs in a subprocess: importing the snapshot puts its `core` package into sys.modules, which other tests import from
+    the live reference tree."""
     sys.path.insert(0, str(ROOT))
-    from oracle import make_ref, oracle as orc, ref_runner
-    from tmcmc202601_b200 import workloads
+    from oracle import make_ref
 
     if not make_ref.build():
         pytest.skip("no reference tree and no oracle/_ref snapshot on this machine")
-    wl = workloads.four_condition_workload(2, seed=11, tsm_variance=False)
-    arm = ref_runner.ReferenceArm(wl.config, n_jobs=2)
-    ll = arm.evaluate_ode_only(wl.theta, wl.cond_id)
-    ref = orc.evaluate_hmx(wl.config, wl.theta, wl.cond_id)
-    assert np.max(np.abs(ll - ref) / np.abs(ref)) < 1e-12
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from oracle import oracle as orc, ref_runner\n"
+        "from tmcmc202601_b200 import workloads\n"
+        "wl = workloads.four_condition_workload(2, seed=11, tsm_variance=False)\n"
+        "arm = ref_runner.ReferenceArm(wl.config, n_jobs=2)\n"
+        "ll = arm.evaluate_ode_only(wl.theta, wl.cond_id)\n"
+        "ref = orc.evaluate_hmx(wl.config, wl.theta, wl.cond_id)\n"
+        "print('MAXREL', float(np.max(np.abs(ll - ref) / np.abs(ref))))\n" % str(ROOT))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    worst = float([l for l in out.stdout.splitlines() if l.startswith("MAXREL")][0].split()[1])
+    assert worst < 1e-12

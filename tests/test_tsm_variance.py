@@ -207,3 +207,31 @@ def test_gpu_full_trajectory_variance_and_all_rows_guard(built):
         e2.close()
     finally:
         eng.close()
+
+
+def test_factor_once_sensitivities_match_oracle_on_the_host():
+    """tsm_row (hmx_obs.cuh: direction_factor once per row + direction_apply per parameter) compiled for the CPU against the
+    oracle's dense sensitivity solve, on rows of oracle trajectories for every condition (incl. early, stiff rows)."""
+    import ctypes as C
+
+    from helpers import dptr, load_emu
+
+    emu = load_emu()
+    wl = workloads.four_condition_workload(3, seed=5)
+    pairs = orc.from_hmx_config(wl.config)
+    worst_x1 = worst_s2 = 0.0
+    for i in range(wl.theta.shape[0]):
+        c = int(wl.cond_id[i])
+        scfg, cc = pairs[c]
+        th = np.ascontiguousarray(wl.theta[i])
+        _, g, *_ = orc.run_deterministic(scfg, th)
+        var = (cc.cov_rel * th) ** 2
+        for t in (1, 2, 40, 339, 1200, 2500):
+            x1o = orc.sensitivity_row(scfg, th, g[t], g[t - 1], cc.active_theta_mask)
+            s2o = (x1o ** 2 * var[None, :]).sum(axis=1) + 1e-12
+            s2, x1 = np.empty(12), np.empty((12, 20))
+            gn, go = np.ascontiguousarray(g[t]), np.ascontiguousarray(g[t - 1])
+            assert emu.emu_tsm_row(C.byref(wl.config), c, dptr(th), dptr(gn), dptr(go), dptr(s2), dptr(x1)) == 1
+            worst_x1 = max(worst_x1, _scaled(x1, x1o))
+            worst_s2 = max(worst_s2, float((np.abs(s2 - s2o) / s2o).max()))
+    assert worst_x1 < REL and worst_s2 < REL, (worst_x1, worst_s2)

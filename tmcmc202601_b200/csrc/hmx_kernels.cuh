@@ -28,6 +28,9 @@ namespace hmx {
 #ifndef HMX_ODE_MINBLOCKS
 #define HMX_ODE_MINBLOCKS 2
 #endif
+#ifndef HMX_OBS_MINBLOCKS
+#define HMX_OBS_MINBLOCKS 1  // resident 128-thread CTAs per SM the observation / TSM-row kernels are compiled for
+#endif
 constexpr int kOdeThreads = HMX_ODE_THREADS;      // 4 warps: one per SM sub-partition
 constexpr int kOdeMinBlocks = HMX_ODE_MINBLOCKS;  // 2 -> 255 registers / thread available, 8 warps / SM
 
@@ -56,8 +59,8 @@ struct OdeParams {
     const double* theta;     // [N,20]
     const int32_t* cond_id;  // [N] or null
     long long N;
-    double* pairs;           // [N, n_obs_max, 24]
-    long long pair_stride;   // n_obs_max * 24
+    double* pairs;           // [n_obs_max, 24, N]: entry (o, j) of evaluation w at pairs[(o * 24 + j) * pair_stride + w]
+    long long pair_stride;   // N of the launch
     double* traj;            // [N, n_steps+1, 12] (or [N, traj_n_rows, 12] with a row map) or null
     const int32_t* traj_row_map;  // [n_steps+1]: output row of time level t, -1 = not stored; null = every level
     int traj_n_rows;
@@ -141,14 +144,17 @@ __global__ void HMX_ODE_BOUNDS ode_kernel(const __grid_constant__ OdeParams P) {
             if (step_idx + 1 == next_t) {
                 // observation row reached: keep (g_t, g_{t-1}) for the sensitivity kernel
                 const OdeCond& oc = P.cond[c];
-                double* pr = P.pairs + w * P.pair_stride;
+                // pairs are stored entry-major ([n_obs_max * 24, N]: consecutive evaluations are adjacent), so that the
+                // observation kernel's one-thread-per-evaluation reads coalesce; these stores happen 5-6 times per evaluation
+                const long long ps = P.pair_stride;
+                double* pr = P.pairs + w;
                 do {
-                    double* q = pr + next_obs * kPairStride;
+                    double* q = pr + (long long)next_obs * kPairStride * ps;
 #pragma unroll
-                    for (int i = 0; i < 12; ++i) q[i] = g[i];
+                    for (int i = 0; i < 12; ++i) q[i * ps] = g[i];
 #pragma unroll
-                    for (int i = 0; i < 11; ++i) q[12 + i] = gp[i];
-                    q[23] = 0.0;
+                    for (int i = 0; i < 11; ++i) q[(12 + i) * ps] = gp[i];
+                    q[23 * ps] = 0.0;
                     ++next_obs;
                     next_t = (next_obs < oc.n_obs) ? max(oc.idx[next_obs], 1) : 0x7fffffff;
                 } while (step_idx + 1 == next_t);
@@ -196,10 +202,11 @@ __global__ void __launch_bounds__(128) resolve_kernel(const __grid_constant__ Od
     int next_obs = 0;
     auto step_end = [&](const double (&g)[12], const RegArr<11>& gp, int step_idx) {
         while (next_obs < oc.n_obs && max(oc.idx[next_obs], 1) == step_idx + 1) {
-            double* q = P.pairs + w * P.pair_stride + next_obs * kPairStride;
-            for (int i = 0; i < 12; ++i) q[i] = g[i];
-            for (int i = 0; i < 11; ++i) q[12 + i] = gp[i];
-            q[23] = 0.0;
+            const long long ps = P.pair_stride;
+            double* q = P.pairs + w + (long long)next_obs * kPairStride * ps;
+            for (int i = 0; i < 12; ++i) q[i * ps] = g[i];
+            for (int i = 0; i < 11; ++i) q[(12 + i) * ps] = gp[i];
+            q[23 * ps] = 0.0;
             ++next_obs;
         }
         if (P.traj) {
@@ -310,7 +317,7 @@ struct ObsParams {
 };
 
 template <bool ALPHA, int HILL>
-__global__ void __launch_bounds__(128) obs_kernel(const __grid_constant__ ObsParams P) {
+__global__ void __launch_bounds__(128, HMX_OBS_MINBLOCKS) obs_kernel(const __grid_constant__ ObsParams P) {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= P.N) return;
     const int c = cond_index(P.cond_id, w, P.n_cond);
@@ -319,11 +326,11 @@ __global__ void __launch_bounds__(128) obs_kernel(const __grid_constant__ ObsPar
 #pragma unroll
     for (int k = 0; k < HMX_NTHETA; ++k) th[k] = __ldg(P.theta + w * HMX_NTHETA + k);
     uint32_t st = 0u;
-    const double ll = obs_loglik<ALPHA, HILL>(P.K, C, P.TM, th, P.pairs + w * P.pair_stride, P.status_in[w],
+    const double ll = obs_loglik<ALPHA, HILL>(P.K, C, P.TM, th, P.pairs + w, P.status_in[w],
                                               P.obs_state ? P.obs_state + w * P.obs_stride : nullptr, &st,
                                               P.sigma2 ? P.sigma2 + w * P.obs_stride : nullptr,
                                               P.x1 ? P.x1 + w * P.obs_stride * HMX_NTHETA : nullptr,
-                                              P.pull ? P.pull + w * (P.obs_stride / 12) * 5 : nullptr);
+                                              P.pull ? P.pull + w * (P.obs_stride / 12) * 5 : nullptr, P.pair_stride);
     const bool okc = cond_valid(P.cond_id, w, P.n_cond);
     P.logL[w] = okc ? ll : -1e20;
     if (P.status_out) P.status_out[w] = okc ? st : (st | kStBadCond);
@@ -347,7 +354,7 @@ struct TsmRowsParams {
 };
 
 template <bool ALPHA, int HILL>
-__global__ void __launch_bounds__(128) tsm_rows_kernel(const __grid_constant__ TsmRowsParams P) {
+__global__ void __launch_bounds__(128, HMX_OBS_MINBLOCKS) tsm_rows_kernel(const __grid_constant__ TsmRowsParams P) {
     const int T = P.K.n_steps;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long w = tid / T;

@@ -23,7 +23,8 @@ struct ThetaMap {
 #define HMX_THETA_P {0, 0, 1, 0, 1, 2, 2, 3, 2, 3, 0, 0, 1, 1, 4, 4, 0, 1, 2, 3}
 #define HMX_THETA_Q {0, 1, 1, -1, -1, 2, 3, 3, -1, -1, 2, 3, 2, 3, 4, -1, 4, 4, 4, 4}
 
-// pair = [g_t (12), phi_old(5), phi0_old, psi_old(5), pad] for t = max(idx,1); 24 doubles per observation row
+// pair = [g_t (12), phi_old(5), phi0_old, psi_old(5), pad] for t = max(idx,1); 24 doubles per observation row (device scratch:
+// entry-major over the evaluations of a launch, see obs_loglik's pair_step)
 constexpr int kPairStride = 24;
 
 // TSM variance of ONE trajectory row (S4:1095-1150): x = g_t, gp = g_{t-1} (first 11 entries).  sig2[12] receives
@@ -36,6 +37,10 @@ HMX_HD bool tsm_row(const SolverConsts& K, const CondConsts& C, const ThetaMap& 
     bool ok = true;
     Eval e;
     residual<ALPHA, HILL>(K, x, gp, A, b, e);  // clipped copies, as compute_Jacobian_matrix does (S5:734-758)
+    // every sensitivity system of this row has the same matrix: factor it once (direction_factor), then one cheap solve per
+    // active parameter; a row whose elimination meets a small pivot keeps the full (pivoting) direction() per parameter
+    DirFactor F;
+    direction_factor<ALPHA, HILL>(K, e, A, b, F);
     for (int k = 0; k < HMX_NTHETA; ++k) {
         if (!((C.active_theta_mask >> k) & 1u)) continue;
         const int p = TM.p[k], q = TM.q[k];
@@ -65,7 +70,8 @@ HMX_HD bool tsm_row(const SolverConsts& K, const CondConsts& C, const ThetaMap& 
             }
         }
         double x1[12];
-        direction<ALPHA, HILL>(K, e, A, b, x1);
+        if (F.healthy) direction_apply<HILL>(e, A, F, e.Q, x1);
+        else direction<ALPHA, HILL>(K, e, A, b, x1);
         if (x1_out) {
 #pragma unroll
             for (int i = 0; i < 12; ++i) x1_out[(size_t)i * HMX_NTHETA + k] = x1[i];
@@ -89,7 +95,7 @@ HMX_HD bool tsm_row(const SolverConsts& K, const CondConsts& C, const ThetaMap& 
 template <bool ALPHA, int HILL>
 HMX_HD double obs_loglik(const SolverConsts& K, const CondConsts& C, const ThetaMap& TM, const double* theta,
                          const double* pairs, uint32_t solve_status, double* obs_state, uint32_t* status_out,
-                         double* sig2_out = nullptr, double* x1_out = nullptr, double* pull_out = nullptr) {
+                         double* sig2_out = nullptr, double* x1_out = nullptr, double* pull_out = nullptr, long long pair_step = 1) {
     double A[15], b[5];
     theta_to_Ab(theta, A, b);
     bool bad = (solve_status & kStNonfinite) != 0u;
@@ -98,11 +104,13 @@ HMX_HD double obs_loglik(const SolverConsts& K, const CondConsts& C, const Theta
 
     for (int o = 0; o < C.n_obs; ++o) {
         double x[12], gp[11];
-        const double* pr = pairs + (size_t)o * kPairStride;
+        // pair_step: distance between consecutive entries of one evaluation's pairs (1: a private contiguous block; N: the
+        // kernels' entry-major scratch, where consecutive evaluations are adjacent and a warp's reads coalesce)
+        const double* pr = pairs + (long long)o * kPairStride * pair_step;
 #pragma unroll
-        for (int i = 0; i < 12; ++i) x[i] = pr[i];
+        for (int i = 0; i < 12; ++i) x[i] = pr[i * pair_step];
 #pragma unroll
-        for (int i = 0; i < 11; ++i) gp[i] = pr[12 + i];
+        for (int i = 0; i < 11; ++i) gp[i] = pr[(12 + i) * pair_step];
         double state[12];  // g_arr[idx]; differs from the pair's g_t only for idx == 0 (S4:1139-1141)
 #pragma unroll
         for (int i = 0; i < 12; ++i) state[i] = (C.idx[o] == 0) ? C.g0[i] : x[i];
