@@ -19,8 +19,11 @@
  *     full PCIe rate); a call with any host OUTPUT pointer returns after the
  *     results have landed (stream-synchronised); a call whose outputs are all device pointers only
  *     enqueues work on the context stream (hmx_set_stream / hmx_synchronize).
- *   - one context per process and GPU; calls on one context serialise (not thread-safe, like the
- *     reference evaluator whose histories are mutable).
+ *   - calls on one context serialise (not thread-safe, like the reference evaluator whose histories are
+ *     mutable).  Several contexts may live on one GPU, one host thread each: every context owns a
+ *     non-blocking stream and takes its scratch memory from the stream-ordered allocator
+ *     (cudaMallocAsync / cudaFreeAsync), so creating, growing or destroying one context never
+ *     synchronises the device under another context's running kernels.
  *   - failed solves follow the reference's error convention: logL = -1e20, never an error return
  *     (EV:655,667,753; TM:306).
  *   - there is NO CPU fallback: hmx_create fails when no sm_100 device is present.
