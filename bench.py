@@ -412,8 +412,13 @@ def tmcmc_runs(local_rank: int) -> dict:
         (h, hs, _), ck = clocked(lambda: rp.run_condition("Commensal_Static", 1000, 2, device_mutation=False))
         (d, ds, _), _ = clocked(lambda: rp.run_condition("Commensal_Static", 1000, 2, device_mutation=True))
         act = workloads.load_conditions()["Commensal_Static"]["active_indices"]
+        # the two chains advanced together through merged launches (batch.run_batch_TMCMC): same samples as chain after chain
+        (mm, mo), _ = clocked(lambda: rp.run_merged(["Commensal_Static"], 1000, 2, device_mutation=True))
+        merged_equal = bool(np.array_equal(np.concatenate(mo[0]["chains"]), ds))
         out["configs0_commensal_static"] = {
-            "host_mutation_wall_s": h["wall_s"], "device_mutation_wall_s": d["wall_s"], "likelihood_evaluations": h["likelihood_evaluations"],
+            "host_mutation_wall_s": h["wall_s"], "device_mutation_wall_s": d["wall_s"],
+            "device_mutation_merged_chains_wall_s": mm["wall_s"], "merged_launches": mm["merged_launches"],
+            "merged_samples_equal_sequential": merged_equal, "likelihood_evaluations": h["likelihood_evaluations"],
             "stages": h["stages"], "converged": h["converged"], "logL_max": [h["logL_max"], d["logL_max"]],
             "posterior_z_host_vs_device_max": z_between(hs[:, act], ds[:, act]), "clocks": ck}
     except Exception as e:  # noqa: BLE001
