@@ -1,9 +1,10 @@
-"""Scheduling study of the ODE kernel's per-lane state machine (CPU only).
+"""Per-trip event traces of the ODE kernel's lane state machine (CPU only).
 
-Records, through the host compile of the product headers (tests/csrc/host_emu.cpp: emu_trip_trace), what every trip of
-an evaluation did (direction solved? time step ended?) for prior draws of the bench workload, then replays warps of 32
-lanes under different step-end policies with a warp-instruction cost model taken from the ncu source attribution
-(DESIGN.md section 4).  Usage: python scripts/trip_sim.py [n_per_condition]
+Records, through the host compile of the product headers (tests/csrc/host_emu.cpp: emu_trip_trace), what every trip of an
+evaluation did (direction solved? time step ended?) for prior draws of the bench workload and prints the statistics the warp
+cost estimates of DESIGN.md section 8 start from: directions and step ends per trip, trips per time step.  The launch-level
+replay (arrival order / longest first / processor sharing) is scripts/schedule_replay.py.
+Usage: python scripts/trip_sim.py [n_per_condition]
 """
 import ctypes as C
 import sys
