@@ -299,7 +299,7 @@ int run_chunk(hmx_ctx* ctx, const double* d_theta, const int32_t* d_cond, long l
     P.cond_id = d_cond;
     P.N = N;
     P.pairs = (double*)ctx->pairs.p;
-    P.pair_stride = N;  // entry-major: [n_obs_max * 24, N]
+    P.pair_stride = pair_stride;
     P.traj = d_traj;
     P.traj_row_map = ctx->cur_row_map;
     P.traj_n_rows = ctx->cur_row_map ? ctx->cur_n_rows : ctx->cfg.n_steps + 1;
@@ -391,7 +391,7 @@ int run_chunk(hmx_ctx* ctx, const double* d_theta, const int32_t* d_cond, long l
         O.cond_id = d_cond;
         O.N = N;
         O.pairs = (const double*)ctx->pairs.p;
-        O.pair_stride = N;
+        O.pair_stride = pair_stride;
         O.status_in = d_status;
         O.status_out = d_status;
         O.logL = d_logL;

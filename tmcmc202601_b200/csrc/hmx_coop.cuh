@@ -479,21 +479,20 @@ __global__ void __launch_bounds__(kCoopThreads) coop_ode_kernel(const __grid_con
                 // g_* = g_arr[step_idx + 1], gp_* = g_arr[step_idx]
                 if (step_idx + 1 == next_t) {
                     const OdeCond& oc = P.cond[c];
-                    const long long ps = P.pair_stride;  // entry-major pairs, see ode_kernel
-                    double* pr = P.pairs + w;
+                    double* pr = P.pairs + w * P.pair_stride;
                     do {
-                        double* q = pr + (long long)next_obs * kPairStride * ps;
+                        double* q = pr + next_obs * kPairStride;
                         if (sp) {
-                            q[role * ps] = g_ph;
-                            q[(6 + role) * ps] = g_ps;
-                            q[(12 + role) * ps] = gp_ph;
-                            q[(18 + role) * ps] = gp_ps;
+                            q[role] = g_ph;
+                            q[6 + role] = g_ps;
+                            q[12 + role] = gp_ph;
+                            q[18 + role] = gp_ps;
                         } else if (role == 5) {
-                            q[5 * ps] = g_ph;
-                            q[11 * ps] = g_ps;
-                            q[17 * ps] = gp_ph;
+                            q[5] = g_ph;
+                            q[11] = g_ps;
+                            q[17] = gp_ph;
                         } else if (role == 6) {
-                            q[23 * ps] = 0.0;
+                            q[23] = 0.0;
                         }
                         ++next_obs;
                         next_t = (next_obs < oc.n_obs) ? max(oc.idx[next_obs], 1) : 0x7fffffff;

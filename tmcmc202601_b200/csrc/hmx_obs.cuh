@@ -23,8 +23,7 @@ struct ThetaMap {
 #define HMX_THETA_P {0, 0, 1, 0, 1, 2, 2, 3, 2, 3, 0, 0, 1, 1, 4, 4, 0, 1, 2, 3}
 #define HMX_THETA_Q {0, 1, 1, -1, -1, 2, 3, 3, -1, -1, 2, 3, 2, 3, 4, -1, 4, 4, 4, 4}
 
-// pair = [g_t (12), phi_old(5), phi0_old, psi_old(5), pad] for t = max(idx,1); 24 doubles per observation row (device scratch:
-// entry-major over the evaluations of a launch, see obs_loglik's pair_step)
+// pair = [g_t (12), phi_old(5), phi0_old, psi_old(5), pad] for t = max(idx,1); 24 doubles per observation row
 constexpr int kPairStride = 24;
 
 // TSM variance of ONE trajectory row (S4:1095-1150): x = g_t, gp = g_{t-1} (first 11 entries).  sig2[12] receives
@@ -95,7 +94,7 @@ HMX_HD bool tsm_row(const SolverConsts& K, const CondConsts& C, const ThetaMap& 
 template <bool ALPHA, int HILL>
 HMX_HD double obs_loglik(const SolverConsts& K, const CondConsts& C, const ThetaMap& TM, const double* theta,
                          const double* pairs, uint32_t solve_status, double* obs_state, uint32_t* status_out,
-                         double* sig2_out = nullptr, double* x1_out = nullptr, double* pull_out = nullptr, long long pair_step = 1) {
+                         double* sig2_out = nullptr, double* x1_out = nullptr, double* pull_out = nullptr) {
     double A[15], b[5];
     theta_to_Ab(theta, A, b);
     bool bad = (solve_status & kStNonfinite) != 0u;
@@ -104,13 +103,11 @@ HMX_HD double obs_loglik(const SolverConsts& K, const CondConsts& C, const Theta
 
     for (int o = 0; o < C.n_obs; ++o) {
         double x[12], gp[11];
-        // pair_step: distance between consecutive entries of one evaluation's pairs (1: a private contiguous block; N: the
-        // kernels' entry-major scratch, where consecutive evaluations are adjacent and a warp's reads coalesce)
-        const double* pr = pairs + (long long)o * kPairStride * pair_step;
+        const double* pr = pairs + (size_t)o * kPairStride;
 #pragma unroll
-        for (int i = 0; i < 12; ++i) x[i] = pr[i * pair_step];
+        for (int i = 0; i < 12; ++i) x[i] = pr[i];
 #pragma unroll
-        for (int i = 0; i < 11; ++i) gp[i] = pr[(12 + i) * pair_step];
+        for (int i = 0; i < 11; ++i) gp[i] = pr[12 + i];
         double state[12];  // g_arr[idx]; differs from the pair's g_t only for idx == 0 (S4:1139-1141)
 #pragma unroll
         for (int i = 0; i < 12; ++i) state[i] = (C.idx[o] == 0) ? C.g0[i] : x[i];
